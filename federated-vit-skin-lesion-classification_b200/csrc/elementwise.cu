@@ -1,0 +1,208 @@
+// elementwise.cu — the small HBM-bound helpers around the GEMMs: patch gather, cls/pos rows,
+// column sums (bias / pos_embed / cls_token gradients) and the fp32 row softmax of the parity path.
+//
+// Reference call sites: timm PatchEmbed (Conv2d k=16,s=16 -> flatten -> transpose), the
+// cat(cls_token, x) + pos_embed prologue of VisionTransformer.forward, and the bias terms of
+// every nn.Linear — all reached from model.py:193; their gradients from train.py:153.
+#include "common.cuh"
+
+namespace fv {
+
+// out[(b, ph, pw), (c, py, px)] = img[b, c, ph*16+py, pw*16+px]; one thread moves 4 px.
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int chans,
+                int height, int width) {
+  const int gw = width >> 4, gh = height >> 4;
+  const int kdim = chans * 256;
+  const long long total = static_cast<long long>(batch) * gh * gw * (kdim >> 2);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kq = static_cast<int>(i % (kdim >> 2));
+    const long long row = i / (kdim >> 2);
+    const int pw = static_cast<int>(row % gw);
+    const int ph = static_cast<int>((row / gw) % gh);
+    const int b = static_cast<int>(row / (static_cast<long long>(gw) * gh));
+    const int px = (kq & 3) << 2;
+    const int py = (kq >> 2) & 15;
+    const int c = kq >> 6;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(
+        img + ((static_cast<long long>(b) * chans + c) * height + (ph * 16 + py)) * width + pw * 16 + px));
+    if (OUT_BF16) {
+      uint2 pk;
+      pk.x = pack_bf16(v.x, v.y);
+      pk.y = pack_bf16(v.z, v.w);
+      reinterpret_cast<uint2*>(out)[i] = pk;
+    } else {
+      reinterpret_cast<float4*>(out)[i] = v;
+    }
+  }
+}
+
+// x[b, 0, :] = cls + pos[0, :]
+__global__ void __launch_bounds__(256)
+cls_pos_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
+               int batch, long long tokens, int dim) {
+  const int total = batch * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / dim, d = i - b * dim;
+    x[static_cast<long long>(b) * tokens * dim + d] = cls[d] + pos[d];
+  }
+}
+
+// out[c] += sum_r a[r, c].  block = 32 x 8; a warp row covers 64 columns (2 per lane).
+template <bool IN_BF16>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ a, long long lda, float* __restrict__ out, long long rows,
+              int cols, int rows_per_block) {
+  __shared__ float2 red[8][32];
+  const int col = blockIdx.x * 64 + threadIdx.x * 2;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float2 s = make_float2(0.f, 0.f);
+  if (col < cols) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      if (IN_BF16) {
+        const uint32_t u = __ldcs(reinterpret_cast<const uint32_t*>(
+            reinterpret_cast<const __nv_bfloat16*>(a) + r * lda + col));
+        const float2 f = unpack_bf16(u);
+        s.x += f.x;
+        s.y += f.y;
+      } else {
+        const float2 f = __ldcs(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a) + r * lda + col));
+        s.x += f.x;
+        s.y += f.y;
+      }
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < cols) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      s.x += red[j][threadIdx.x].x;
+      s.y += red[j][threadIdx.x].y;
+    }
+    atomicAdd(out + col, s.x);
+    atomicAdd(out + col + 1, s.y);
+  }
+}
+
+// p = softmax(scale * s) row-wise; one warp per row (fp32 parity path of the attention core)
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, float* __restrict__ p, long long rows, int cols,
+                    float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* sr = s + row * cols;
+  float* pr = p + row * cols;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, sr[c] * scale);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += expf(sr[c] * scale - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int c = lane; c < cols; c += 32) pr[c] = expf(sr[c] * scale - mx) * inv;
+}
+
+// ds = scale * p * (dp - sum(dp * p))
+__global__ void __launch_bounds__(256)
+softmax_rows_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp,
+                        float* __restrict__ ds, long long rows, int cols, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* pr = p + row * cols;
+  const float* dr = dp + row * cols;
+  float dot = 0.f;
+  for (int c = lane; c < cols; c += 32) dot += pr[c] * dr[c];
+  dot = warp_sum(dot);
+  for (int c = lane; c < cols; c += 32) ds[row * cols + c] = scale * pr[c] * (dr[c] - dot);
+}
+
+}  // namespace fv
+
+extern "C" int fv_patchify(const float* img, void* out, int out_dtype, int64_t batch, int64_t chans,
+                           int64_t height, int64_t width, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(img && out, "fv_patchify: null pointer");
+  FV_CHECK_ARG(batch > 0 && chans > 0 && height > 0 && width > 0 && height % 16 == 0 && width % 16 == 0,
+               "fv_patchify: image %lldx%lldx%lldx%lld must have H, W multiples of 16",
+               (long long)batch, (long long)chans, (long long)height, (long long)width);
+  FV_CHECK_ARG(out_dtype == FV_F32 || out_dtype == FV_BF16, "fv_patchify: bad out_dtype");
+  FV_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "fv_patchify: pointers must be 16-byte aligned");
+  const long long total = batch * (height / 16) * (width / 16) * chans * 64;
+  long long want = ceil_div(total, 256 * 4);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  const unsigned grid = static_cast<unsigned>(want < cap ? (want < 1 ? 1 : want) : cap);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (out_dtype == FV_BF16)
+    patchify_kernel<true><<<grid, 256, 0, st>>>(img, out, (int)batch, (int)chans, (int)height, (int)width);
+  else
+    patchify_kernel<false><<<grid, 256, 0, st>>>(img, out, (int)batch, (int)chans, (int)height, (int)width);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_cls_pos_rows(const float* cls, const float* pos, float* x, int64_t batch,
+                               int64_t tokens, int64_t dim, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(cls && pos && x && batch > 0 && tokens > 0 && dim > 0 && batch * dim < (1LL << 31),
+               "fv_cls_pos_rows: bad argument");
+  const unsigned grid = static_cast<unsigned>(ceil_div(batch * dim, 256));
+  cls_pos_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(cls, pos, x, (int)batch, tokens, (int)dim);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_colsum(const void* a, int a_dtype, int64_t lda, float* out, int accumulate,
+                         int64_t rows, int64_t cols, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(a && out && rows >= 0 && cols > 0 && cols % 2 == 0 && lda % 2 == 0 && cols < (1LL << 30),
+               "fv_colsum: bad argument (cols and lda must be even)");
+  FV_CHECK_ARG(a_dtype == FV_F32 || a_dtype == FV_BF16, "fv_colsum: bad dtype");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!accumulate) FV_CHECK_CUDA(cudaMemsetAsync(out, 0, cols * sizeof(float), st));
+  if (rows == 0) return FV_OK;
+  const int col_blocks = static_cast<int>(ceil_div(cols, 64));
+  // enough row slices to fill the machine, at least 64 rows each
+  int64_t slices = ceil_div(static_cast<int64_t>(num_sms()) * 8, col_blocks);
+  int64_t rows_per = ceil_div(rows, slices);
+  if (rows_per < 64) rows_per = 64;
+  slices = ceil_div(rows, rows_per);
+  dim3 grid(col_blocks, static_cast<unsigned>(slices));
+  dim3 block(32, 8);
+  if (a_dtype == FV_BF16)
+    colsum_kernel<true><<<grid, block, 0, st>>>(a, lda, out, rows, (int)cols, (int)rows_per);
+  else
+    colsum_kernel<false><<<grid, block, 0, st>>>(a, lda, out, rows, (int)cols, (int)rows_per);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_softmax_rows(const float* s, float* p, int64_t rows, int64_t cols, float scale,
+                               void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(s && p && rows >= 0 && cols > 0 && cols < (1LL << 30), "fv_softmax_rows: bad argument");
+  if (rows == 0) return FV_OK;
+  softmax_rows_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      s, p, rows, (int)cols, scale);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_softmax_rows_bwd(const float* p, const float* dp, float* ds, int64_t rows,
+                                   int64_t cols, float scale, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(p && dp && ds && rows >= 0 && cols > 0 && cols < (1LL << 30),
+               "fv_softmax_rows_bwd: bad argument");
+  if (rows == 0) return FV_OK;
+  softmax_rows_bwd_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, dp, ds, rows, (int)cols, scale);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}

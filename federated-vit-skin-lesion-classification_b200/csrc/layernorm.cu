@@ -1,0 +1,237 @@
+// layernorm.cu — fused LayerNorm forward / backward (HBM-bound; one warp per row).
+//
+// Replaces F.layer_norm behind timm's Block.norm1 / norm2 and VisionTransformer.norm (reference
+// call site model.py:193) and its autograd backward (train.py:153). Statistics are fp32 whatever
+// the output type, as under autocast.
+//
+// Algorithmic bytes per row of D columns:
+//   fwd: 4D (x) + sizeof(y)·D + 8 (mean,rstd)          bwd: sizeof(dy)·D + 4D (x) + 4D (dres)
+//                                                           + 4D (dx) [+ 2D dx_lp] + 8
+#include "common.cuh"
+
+namespace fv {
+
+constexpr int LN_MAX_VEC = 8;     // float4 per lane -> D <= 1024
+constexpr int LN_WARPS = 8;       // rows per CTA pass
+
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, void* __restrict__ y, float* __restrict__ mean,
+                     float* __restrict__ rstd, long long rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = cols >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+  float4 v[LN_MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      v[i] = __ldcs(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mu = warp_sum(s) / cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float a = v[i].x - mu, b = v[i].y - mu, d = v[i].z - mu, e = v[i].w - mu;
+      q += (a * a + b * b) + (d * d + e * e);
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / cols + eps);
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float4 o;
+      o.x = (v[i].x - mu) * rs * g.x + b.x;
+      o.y = (v[i].y - mu) * rs * g.y + b.y;
+      o.z = (v[i].z - mu) * rs * g.z + b.z;
+      o.w = (v[i].w - mu) * rs * g.w + b.w;
+      if (OUT_BF16) {
+        uint2 pk;
+        pk.x = pack_bf16(o.x, o.y);
+        pk.y = pack_bf16(o.z, o.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * cols)[c] = pk;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * cols)[c] = o;
+      }
+    }
+  }
+}
+
+// Backward. Each warp walks rows with a grid stride and keeps its slice of dgamma / dbeta in
+// registers; one shared-memory reduction and one atomicAdd per column per CTA at the end.
+template <bool DY_BF16>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
+                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ dres,
+                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_lp,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
+                     int cols) {
+  extern __shared__ float red[];  // [LN_WARPS][cols] twice
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nvec = cols >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float4 gam[LN_MAX_VEC], dg[LN_MAX_VEC], db[LN_MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = lane + 32 * i;
+    gam[i] = c < nvec ? __ldg(g4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_cols = 1.0f / cols;
+  for (long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp; row < rows;
+       row += static_cast<long long>(gridDim.x) * LN_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+    float4 xh[LN_MAX_VEC], gy[LN_MAX_VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 xv = __ldcs(xr + c);
+        float4 d;
+        if (DY_BF16) {
+          const uint2 pk = __ldcs(
+              reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + row * cols) + c);
+          const float2 lo = unpack_bf16(pk.x), hi = unpack_bf16(pk.y);
+          d = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          d = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * cols) + c);
+        }
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        gy[i] = make_float4(d.x * gam[i].x, d.y * gam[i].y, d.z * gam[i].z, d.w * gam[i].w);
+        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y;
+        dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+        s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+      }
+    }
+    s1 = warp_sum(s1) * inv_cols;
+    s2 = warp_sum(s2) * inv_cols;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float4 o;
+        o.x = rs * (gy[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (gy[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (gy[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (gy[i].w - s1 - xh[i].w * s2);
+        if (dres != nullptr) {
+          const float4 r = __ldcs(reinterpret_cast<const float4*>(dres + row * cols) + c);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        reinterpret_cast<float4*>(dx + row * cols)[c] = o;
+        if (dx_lp != nullptr) {
+          uint2 pk;
+          pk.x = pack_bf16(o.x, o.y);
+          pk.y = pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(dx_lp + row * cols)[c] = pk;
+        }
+      }
+    }
+  }
+  // CTA reduction of the per-warp dgamma / dbeta slices
+  float* red_g = red;
+  float* red_b = red + LN_WARPS * cols;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      reinterpret_cast<float4*>(red_g + warp * cols)[c] = dg[i];
+      reinterpret_cast<float4*>(red_b + warp * cols)[c] = db[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) {
+      sg += red_g[w * cols + c];
+      sb += red_b[w * cols + c];
+    }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
+}  // namespace fv
+
+extern "C" int fv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y,
+                                int y_dtype, float* mean, float* rstd, int64_t rows, int64_t cols,
+                                float eps, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(x && gamma && beta && y && mean && rstd, "fv_layernorm_fwd: null pointer");
+  FV_CHECK_ARG(rows >= 0 && cols > 0 && cols % 4 == 0 && cols <= LN_MAX_VEC * 128,
+               "fv_layernorm_fwd: cols=%lld must be a multiple of 4 and <= %d", (long long)cols,
+               LN_MAX_VEC * 128);
+  FV_CHECK_ARG(y_dtype == FV_F32 || y_dtype == FV_BF16, "fv_layernorm_fwd: bad y_dtype");
+  if (rows == 0) return FV_OK;
+  const unsigned grid = static_cast<unsigned>(ceil_div(rows, LN_WARPS));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (y_dtype == FV_BF16)
+    layernorm_fwd_kernel<true><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows,
+                                                               (int)cols, eps);
+  else
+    layernorm_fwd_kernel<false><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows,
+                                                                (int)cols, eps);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
+                                const float* mean, const float* rstd, const float* dres, float* dx,
+                                void* dx_lp, float* dgamma, float* dbeta, int64_t rows, int64_t cols,
+                                void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta,
+               "fv_layernorm_bwd: null pointer");
+  FV_CHECK_ARG(rows >= 0 && cols > 0 && cols % 4 == 0 && cols <= LN_MAX_VEC * 128,
+               "fv_layernorm_bwd: cols=%lld must be a multiple of 4 and <= %d", (long long)cols,
+               LN_MAX_VEC * 128);
+  FV_CHECK_ARG(dy_dtype == FV_F32 || dy_dtype == FV_BF16, "fv_layernorm_bwd: bad dy_dtype");
+  if (rows == 0) return FV_OK;
+  int64_t want = ceil_div(rows, LN_WARPS);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
+  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+  const size_t smem = 2 * LN_WARPS * cols * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool configured = false;
+  if (!configured) {
+    FV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * LN_MAX_VEC * 128 * 4));
+    FV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * LN_MAX_VEC * 128 * 4));
+    configured = true;
+  }
+  if (dy_dtype == FV_BF16)
+    layernorm_bwd_kernel<true><<<grid, LN_WARPS * 32, smem, st>>>(
+        dy, x, gamma, mean, rstd, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_lp), dgamma, dbeta,
+        rows, (int)cols);
+  else
+    layernorm_bwd_kernel<false><<<grid, LN_WARPS * 32, smem, st>>>(
+        dy, x, gamma, mean, rstd, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_lp), dgamma, dbeta,
+        rows, (int)cols);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}

@@ -1,0 +1,364 @@
+"""``torch.library`` custom ops (namespace ``fedvit``) over the libfedvit C ABI.
+
+Each op is a thin shim: check shapes/dtypes, allocate outputs with ``torch.empty`` (so PyTorch's
+caching allocator and stream semantics own every buffer), pass raw device pointers plus the
+current CUDA stream through ctypes into ``include/fedvit.h``. There is no eager/CPU fallback: a
+CPU tensor or a missing library raises.
+
+The ops are forward primitives *and* backward primitives (``layernorm_bwd``, ``attention_bwd``,
+the dgrad / wgrad GEMM modes). Autograd is wired one level up, in ``vit.py`` and ``losses.py``,
+where the saved-activation lifetime is managed explicitly.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from ._lib import LIB, FedVitError
+
+F32, BF16 = 0, 1
+EPI = {"none": 0, "residual": 1, "gelu": 2, "dgelu": 3, "accum": 4, "patch": 5}
+MAJOR_K, MAJOR_MN = 0, 1
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise FedVitError(f"unsupported dtype {t.dtype}")
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise FedVitError(
+                "fedvit ops run on CUDA (sm_100a) only — there is no CPU fallback on this path"
+            )
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fedvit::gemm", mutates_args=("out", "aux"))
+def gemm(
+    a: Tensor,
+    b: Tensor,
+    bias: Optional[Tensor],
+    out: Tensor,
+    aux: Optional[Tensor],
+    a_major: int,
+    b_major: int,
+    epilogue: int,
+    split_k: int,
+    tokens_per_img: int,
+) -> None:
+    """out[M,N] = op(a)[M,K] @ op(b)[N,K]^T with a fused epilogue (see include/fedvit.h).
+
+    ``a_major`` / ``b_major``: 0 = the operand is stored [rows, K]; 1 = stored [K, rows].
+    bf16 operands run on tcgen05 tensor cores, fp32 operands on the FFMA parity kernel.
+    """
+    _need_cuda(a, b, bias, out, aux)
+    if a.dim() != 2 or b.dim() != 2 or out.dim() != 2:
+        raise FedVitError("gemm: operands must be 2-D")
+    if a.stride(1) != 1 or b.stride(1) != 1 or out.stride(1) != 1:
+        raise FedVitError("gemm: innermost stride must be 1")
+    m, k = (a.shape[0], a.shape[1]) if a_major == MAJOR_K else (a.shape[1], a.shape[0])
+    n, kb = (b.shape[0], b.shape[1]) if b_major == MAJOR_K else (b.shape[1], b.shape[0])
+    if k != kb:
+        raise FedVitError(f"gemm: contraction mismatch {k} vs {kb}")
+    if epilogue == EPI["patch"]:
+        if out.shape[1] != n:
+            raise FedVitError("gemm: patch epilogue output width mismatch")
+    elif tuple(out.shape) != (m, n):
+        raise FedVitError(f"gemm: out is {tuple(out.shape)}, expected {(m, n)}")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != n):
+        raise FedVitError("gemm: bias must be fp32 [N]")
+    ldaux = aux.stride(0) if aux is not None else 0
+    if a.dtype == torch.bfloat16:
+        if b.dtype != torch.bfloat16:
+            raise FedVitError("gemm: mixed operand dtypes")
+        LIB.call(
+            "fv_gemm_bf16", a.data_ptr(), a_major, a.stride(0), b.data_ptr(), b_major, b.stride(0),
+            _ptr(bias), out.data_ptr(), _dt(out), out.stride(0), _ptr(aux), ldaux, m, n, k,
+            epilogue, split_k, tokens_per_img, _stream(a),
+        )
+    else:
+        if a.dtype != torch.float32 or b.dtype != torch.float32 or out.dtype != torch.float32:
+            raise FedVitError("gemm: fp32 path needs fp32 a, b, out")
+        ars, acs = (a.stride(0), 1) if a_major == MAJOR_K else (1, a.stride(0))
+        brs, bcs = (b.stride(0), 1) if b_major == MAJOR_K else (1, b.stride(0))
+        LIB.call(
+            "fv_gemm_f32", a.data_ptr(), ars, acs, 0, b.data_ptr(), brs, bcs, 0, _ptr(bias),
+            out.data_ptr(), out.stride(0), 0, _ptr(aux), ldaux, m, n, k, 1, 1.0, epilogue,
+            tokens_per_img, _stream(a),
+        )
+
+
+@torch.library.custom_op("fedvit::bgemm_f32", mutates_args=("out",))
+def bgemm_f32(
+    a: Tensor, a_strides: List[int], b: Tensor, b_strides: List[int], out: Tensor,
+    out_strides: List[int], m: int, n: int, k: int, batch: int, alpha: float, accumulate: bool,
+) -> None:
+    """Strided-batched fp32 product for the parity attention path.
+
+    out[z](i,j) (+)= alpha * sum_t a[z](i,t) * b[z](j,t); strides are (row, col, batch) for a/b and
+    (row, batch) for out, all in elements from the tensors' data pointers.
+    """
+    _need_cuda(a, b, out)
+    LIB.call(
+        "fv_gemm_f32", a.data_ptr(), a_strides[0], a_strides[1], a_strides[2], b.data_ptr(),
+        b_strides[0], b_strides[1], b_strides[2], None, out.data_ptr(), out_strides[0],
+        out_strides[1], None, 0, m, n, k, batch, alpha, EPI["accum"] if accumulate else EPI["none"],
+        0, _stream(a),
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fedvit::layernorm_fwd", mutates_args=())
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, out_bf16: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(x, gamma, beta)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2:
+        raise FedVitError("layernorm_fwd: x must be a contiguous fp32 [rows, cols] tensor")
+    rows, cols = x.shape
+    y = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    mean = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    LIB.call("fv_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+             _dt(y), mean.data_ptr(), rstd.data_ptr(), rows, cols, eps, _stream(x))
+    return y, mean, rstd
+
+
+@layernorm_fwd.register_fake
+def _(x, gamma, beta, eps, out_bf16):
+    y = x.new_empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    return y, x.new_empty((x.shape[0],)), x.new_empty((x.shape[0],))
+
+
+@torch.library.custom_op("fedvit::layernorm_bwd", mutates_args=("dgamma", "dbeta"))
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor,
+                  dres: Optional[Tensor], dgamma: Tensor, dbeta: Tensor, want_lp: bool) -> Tuple[Tensor, Tensor]:
+    """dx = dres + LN'(dy); dgamma/dbeta are accumulated in place. Returns (dx fp32, dx bf16|empty)."""
+    _need_cuda(dy, x, gamma, mean, rstd, dres, dgamma, dbeta)
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    dx_lp = torch.empty((rows, cols) if want_lp else (0,), device=x.device, dtype=torch.bfloat16)
+    LIB.call("fv_layernorm_bwd", dy.data_ptr(), _dt(dy), x.data_ptr(), gamma.data_ptr(),
+             mean.data_ptr(), rstd.data_ptr(), _ptr(dres), dx.data_ptr(),
+             dx_lp.data_ptr() if want_lp else None, dgamma.data_ptr(), dbeta.data_ptr(), rows, cols,
+             _stream(x))
+    return dx, dx_lp
+
+
+@layernorm_bwd.register_fake
+def _(dy, x, gamma, mean, rstd, dres, dgamma, dbeta, want_lp):
+    return torch.empty_like(x), x.new_empty(x.shape if want_lp else (0,), dtype=torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention core (bf16 flash kernels)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fedvit::attention_fwd", mutates_args=())
+def attention_fwd(qkv: Tensor, batch: int, tokens: int, heads: int, scale: float) -> Tuple[Tensor, Tensor]:
+    """qkv [B*N, 3*H*64] bf16 -> (out [B*N, H*64] bf16, lse [B, H, N] fp32)."""
+    _need_cuda(qkv)
+    if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or qkv.shape != (batch * tokens, 3 * heads * 64):
+        raise FedVitError("attention_fwd: qkv must be contiguous bf16 [B*N, 3*H*64]")
+    out = torch.empty((batch * tokens, heads * 64), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty((batch, heads, tokens), device=qkv.device, dtype=torch.float32)
+    LIB.call("fv_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), BF16, batch, tokens,
+             heads, scale, _stream(qkv))
+    return out, lse
+
+
+@attention_fwd.register_fake
+def _(qkv, batch, tokens, heads, scale):
+    return (qkv.new_empty((batch * tokens, heads * 64)),
+            qkv.new_empty((batch, heads, tokens), dtype=torch.float32))
+
+
+@torch.library.custom_op("fedvit::attention_bwd", mutates_args=())
+def attention_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, batch: int, tokens: int,
+                  heads: int, scale: float) -> Tensor:
+    _need_cuda(qkv, out, dout, lse)
+    if dout.dtype != torch.bfloat16 or not dout.is_contiguous():
+        raise FedVitError("attention_bwd: dout must be contiguous bf16")
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    LIB.call("fv_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+             delta.data_ptr(), dqkv.data_ptr(), BF16, batch, tokens, heads, scale, _stream(qkv))
+    return dqkv
+
+
+@attention_bwd.register_fake
+def _(qkv, out, dout, lse, batch, tokens, heads, scale):
+    return torch.empty_like(qkv)
+
+
+@torch.library.custom_op("fedvit::softmax_rows", mutates_args=())
+def softmax_rows(s: Tensor, scale: float) -> Tensor:
+    _need_cuda(s)
+    p = torch.empty_like(s)
+    cols = s.shape[-1]
+    LIB.call("fv_softmax_rows", s.data_ptr(), p.data_ptr(), s.numel() // cols, cols, scale, _stream(s))
+    return p
+
+
+@softmax_rows.register_fake
+def _(s, scale):
+    return torch.empty_like(s)
+
+
+@torch.library.custom_op("fedvit::softmax_rows_bwd", mutates_args=())
+def softmax_rows_bwd(p: Tensor, dp: Tensor, scale: float) -> Tensor:
+    _need_cuda(p, dp)
+    ds = torch.empty_like(p)
+    cols = p.shape[-1]
+    LIB.call("fv_softmax_rows_bwd", p.data_ptr(), dp.data_ptr(), ds.data_ptr(), p.numel() // cols,
+             cols, scale, _stream(p))
+    return ds
+
+
+@softmax_rows_bwd.register_fake
+def _(p, dp, scale):
+    return torch.empty_like(p)
+
+
+# ------------------------------------------------------------------------------------------------
+# patch embedding helpers, column sums
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fedvit::patchify", mutates_args=())
+def patchify(img: Tensor, out_bf16: bool) -> Tensor:
+    """NCHW fp32 image -> [B*(H/16)*(W/16), C*256] patch rows, (c, py, px) column order."""
+    _need_cuda(img)
+    if img.dtype != torch.float32 or img.dim() != 4:
+        raise FedVitError("patchify: image must be fp32 NCHW")
+    img = img.contiguous()
+    b, c, h, w = img.shape
+    out = torch.empty((b * (h // 16) * (w // 16), c * 256), device=img.device,
+                      dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    LIB.call("fv_patchify", img.data_ptr(), out.data_ptr(), _dt(out), b, c, h, w, _stream(img))
+    return out
+
+
+@patchify.register_fake
+def _(img, out_bf16):
+    b, c, h, w = img.shape
+    return img.new_empty((b * (h // 16) * (w // 16), c * 256),
+                         dtype=torch.bfloat16 if out_bf16 else torch.float32)
+
+
+@torch.library.custom_op("fedvit::cls_pos_rows", mutates_args=("x",))
+def cls_pos_rows(cls: Tensor, pos: Tensor, x: Tensor, batch: int, tokens: int, dim: int) -> None:
+    _need_cuda(cls, pos, x)
+    LIB.call("fv_cls_pos_rows", cls.data_ptr(), pos.data_ptr(), x.data_ptr(), batch, tokens, dim, _stream(x))
+
+
+@torch.library.custom_op("fedvit::colsum", mutates_args=("out",))
+def colsum(a: Tensor, out: Tensor, accumulate: bool) -> None:
+    """out[c] (+)= sum_r a[r, c] — bias / pos_embed / cls_token gradients."""
+    _need_cuda(a, out)
+    if a.dim() != 2 or a.stride(1) != 1 or out.dtype != torch.float32:
+        raise FedVitError("colsum: a must be 2-D row-major, out fp32")
+    LIB.call("fv_colsum", a.data_ptr(), _dt(a), a.stride(0), out.data_ptr(), int(accumulate),
+             a.shape[0], a.shape[1], _stream(a))
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fedvit::asl_loss", mutates_args=())
+def asl_loss(logits: Tensor, targets: Tensor, gamma_neg: float, gamma_pos: float, clip: float,
+             eps: float) -> Tuple[Tensor, Tensor]:
+    """(mean asymmetric-focal loss [scalar], d loss / d logits [B,C]) in one fused pass."""
+    _need_cuda(logits, targets)
+    logits = logits.float().contiguous()
+    targets = targets.to(torch.int64).contiguous()
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    dlogits = torch.empty_like(logits)
+    LIB.call("fv_asl_loss", logits.data_ptr(), targets.data_ptr(), loss.data_ptr(),
+             dlogits.data_ptr(), logits.shape[0], logits.shape[1], gamma_neg, gamma_pos, clip, eps,
+             _stream(logits))
+    return loss, dlogits
+
+
+@asl_loss.register_fake
+def _(logits, targets, gamma_neg, gamma_pos, clip, eps):
+    return logits.new_empty((), dtype=torch.float32), logits.new_empty(logits.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("fedvit::ce_loss", mutates_args=())
+def ce_loss(logits: Tensor, targets: Tensor) -> Tuple[Tensor, Tensor]:
+    _need_cuda(logits, targets)
+    logits = logits.float().contiguous()
+    targets = targets.to(torch.int64).contiguous()
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    dlogits = torch.empty_like(logits)
+    LIB.call("fv_ce_loss", logits.data_ptr(), targets.data_ptr(), loss.data_ptr(),
+             dlogits.data_ptr(), logits.shape[0], logits.shape[1], _stream(logits))
+    return loss, dlogits
+
+
+@ce_loss.register_fake
+def _(logits, targets):
+    return logits.new_empty((), dtype=torch.float32), logits.new_empty(logits.shape, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# flat-arena sweeps: grad norm, AdamW(+EMA+bf16 cast), EMA, FedAvg fold, cast
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fedvit::sumsq", mutates_args=("out",))
+def sumsq(g: Tensor, out: Tensor, accumulate: bool) -> None:
+    _need_cuda(g, out)
+    LIB.call("fv_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), int(accumulate), _stream(g))
+
+
+@torch.library.custom_op("fedvit::adamw_flat", mutates_args=("p", "m", "v", "ema", "p_lp"))
+def adamw_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_lr: Tensor,
+               seg_wd: Tensor, sumsq_: Optional[Tensor], max_norm: float, beta1: float, beta2: float,
+               eps: float, step: int, ema: Optional[Tensor], ema_decay: float,
+               p_lp: Optional[Tensor]) -> None:
+    _need_cuda(p, g, m, v, seg_end, seg_lr, seg_wd, sumsq_, ema, p_lp)
+    LIB.call("fv_adamw_flat", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+             seg_end.data_ptr(), seg_lr.data_ptr(), seg_wd.data_ptr(), seg_end.numel(),
+             _ptr(sumsq_), max_norm, beta1, beta2, eps, step, _ptr(ema), ema_decay, _ptr(p_lp),
+             p.numel(), _stream(p))
+
+
+@torch.library.custom_op("fedvit::scale_by_clip", mutates_args=("x",))
+def scale_by_clip(x: Tensor, sumsq_: Tensor, max_norm: float) -> None:
+    _need_cuda(x, sumsq_)
+    LIB.call("fv_scale_inplace", x.data_ptr(), sumsq_.data_ptr(), max_norm, x.numel(), _stream(x))
+
+
+@torch.library.custom_op("fedvit::ema_update", mutates_args=("shadow",))
+def ema_update(shadow: Tensor, p: Tensor, decay: float) -> None:
+    _need_cuda(shadow, p)
+    LIB.call("fv_ema_update", shadow.data_ptr(), p.data_ptr(), decay, p.numel(), _stream(p))
+
+
+@torch.library.custom_op("fedvit::fedavg_accum", mutates_args=("acc",))
+def fedavg_accum(acc: Tensor, w: Tensor, weight: float, init: bool) -> None:
+    """acc = (init ? 0 : acc) + weight * w over a flat fp32 arena."""
+    _need_cuda(acc, w)
+    if acc.dtype != torch.float32 or w.dtype != torch.float32 or acc.numel() != w.numel():
+        raise FedVitError("fedavg_accum: fp32 arenas of equal length required")
+    LIB.call("fv_fedavg_accum", acc.data_ptr(), w.data_ptr(), weight, int(init), w.numel(), _stream(w))
+
+
+@torch.library.custom_op("fedvit::cast_bf16", mutates_args=("dst",))
+def cast_bf16(src: Tensor, dst: Tensor) -> None:
+    _need_cuda(src, dst)
+    LIB.call("fv_cast_f32_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream(src))

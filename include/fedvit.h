@@ -1,0 +1,190 @@
+/*
+ * fedvit.h — C ABI of libfedvit.so (B200 / sm_100a).
+ *
+ * The reference (apurbaaaa/Federated-Vit-Skin-Lesion-Classification) is pure Python and has no
+ * FFI of its own: its seam for this path is the set of PyTorch calls made by
+ *   model.py:112-117,178-207   (timm ViT backbone + head forward)
+ *   losses.py:41-67            (AsymmetricFocalLoss.forward)
+ *   train.py:144-162           (autocast fwd, backward, clip, AdamW step, EMA)
+ *   utils.py:76-83,192-193     (EMA.update, clip_grad_norm)
+ * Every entry point below replaces one of those library calls (the reference line it stands in
+ * for is cited per function). INTEGRATION.md shows the ctypes / torch.library binding.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, enums; no torch / C++ types in any signature.
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated here.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, and is CUDA-graph capturable.
+ *   - return value: 0 on success, a negative FV_ERR_* code otherwise; fv_last_error() returns a
+ *     thread-local message. Nothing is thrown across the boundary.
+ *   - all matrices are row-major and densely packed unless a leading dimension is given.
+ */
+#ifndef FEDVIT_H_
+#define FEDVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FV_OK 0
+#define FV_ERR_INVALID_ARG (-1)
+#define FV_ERR_CUDA (-2)
+#define FV_ERR_UNSUPPORTED (-3)
+
+/* element types */
+#define FV_F32 0
+#define FV_BF16 1
+
+/* GEMM epilogues (see fv_gemm_bf16 / fv_gemm_f32) */
+#define FV_EPI_NONE 0          /* C = acc (+bias)                                         */
+#define FV_EPI_RESIDUAL 1      /* C = acc (+bias) + R            R fp32, same shape as C   */
+#define FV_EPI_GELU 2          /* C = gelu_erf(acc+bias); C2 = acc+bias (pre-activation)   */
+#define FV_EPI_DGELU 3         /* C = acc * gelu_erf'(AUX)       AUX = saved pre-activation*/
+#define FV_EPI_ACCUM 4         /* C (fp32) += acc                 weight-gradient accumulate*/
+#define FV_EPI_PATCH 5         /* C[row + row/tokens_per_img + 1] = acc + bias + pos[...]   */
+
+/* operand storage for fv_gemm_*:  op(A) is M x K, op(B) is N x K (both "K-major" when 0).   */
+#define FV_MAJOR_K 0           /* stored [rows, K]   (K contiguous)                        */
+#define FV_MAJOR_MN 1          /* stored [K, rows]   (rows contiguous)                     */
+
+int fv_version(void);
+const char* fv_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t fv_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM  C[M,N] = op(A)[M,K] * op(B)[N,K]^T  with a fused epilogue.
+ * Replaces the cuBLAS calls behind timm's nn.Linear layers — Attention.qkv/.proj, Mlp.fc1/.fc2
+ * (reached from model.py:193) — and their autograd backward (train.py:153).
+ *
+ * fv_gemm_bf16: bf16 operands, fp32 accumulate in TMEM (tcgen05.mma, TMA-fed).
+ * fv_gemm_f32 : fp32 operands, fp32 FFMA (the 1e-4 parity path).
+ *   a_major/b_major : FV_MAJOR_K or FV_MAJOR_MN (how the operand is laid out in memory)
+ *   lda/ldb         : leading dimension in elements of the stored matrix
+ *   bias            : fp32 [N] or NULL
+ *   c, c_dtype, ldc : output (FV_F32 or FV_BF16)
+ *   aux             : FV_EPI_RESIDUAL -> fp32 residual [M,ldaux]; FV_EPI_DGELU -> pre-activation
+ *                     (c_dtype) [M,ldaux]; FV_EPI_GELU -> second output (pre-activation, c_dtype);
+ *                     FV_EPI_PATCH -> fp32 pos_embed [(tokens_per_img+1), N]
+ *   split_k         : >1 only with FV_EPI_ACCUM: K is cut in split_k slices, each atomically
+ *                     accumulated into fp32 C.
+ *   batch / strides : fv_gemm_f32 only (strided-batched, used by the fp32 attention path).
+ * ---------------------------------------------------------------------------------------- */
+int fv_gemm_bf16(const void* a, int a_major, int64_t lda,
+                 const void* b, int b_major, int64_t ldb,
+                 const float* bias,
+                 void* c, int c_dtype, int64_t ldc,
+                 void* aux, int64_t ldaux,
+                 int64_t m, int64_t n, int64_t k,
+                 int epilogue, int split_k, int tokens_per_img, void* stream);
+
+int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_stride, int64_t a_batch_stride,
+                const float* b, int64_t b_row_stride, int64_t b_col_stride, int64_t b_batch_stride,
+                const float* bias,
+                float* c, int64_t ldc, int64_t c_batch_stride,
+                float* aux, int64_t ldaux,
+                int64_t m, int64_t n, int64_t k, int64_t batch,
+                float alpha, int epilogue, int tokens_per_img, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension (eps inside the sqrt, affine).
+ * Replaces timm Block.norm1/norm2 and VisionTransformer.norm (F.layer_norm, model.py:193).
+ *   x fp32 [rows, cols]; y is y_dtype; mean/rstd fp32 [rows] are saved for the backward.
+ * Backward: dx = dres + LN'(dy) in fp32, optional bf16 copy of dx (dx_lp) for the next GEMM;
+ *   dgamma/dbeta are ACCUMULATED (+=) into fp32 [cols] (zero them first for a fresh gradient).
+ * ---------------------------------------------------------------------------------------- */
+int fv_layernorm_fwd(const float* x, const float* gamma, const float* beta,
+                     void* y, int y_dtype, float* mean, float* rstd,
+                     int64_t rows, int64_t cols, float eps, void* stream);
+int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
+                     const float* mean, const float* rstd, const float* dres,
+                     float* dx, void* dx_lp, float* dgamma, float* dbeta,
+                     int64_t rows, int64_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-head self-attention core, softmax(Q K^T * scale) V, no mask, no dropout.
+ * Replaces F.scaled_dot_product_attention inside timm Attention.forward (model.py:193).
+ *   qkv : [B, N, 3, H, 64] (the un-permuted output of Attention.qkv), dtype bf16 or fp32
+ *   out : [B, N, H, 64] token-major (what Attention.proj consumes)
+ *   lse : fp32 [B, H, N] log-sum-exp of the scaled scores, saved for the backward
+ * Backward writes dqkv in the same [B, N, 3, H, 64] layout.
+ *   delta: fp32 [B, H, N] scratch (rowsum(dO * O)), caller-owned.
+ * head_dim is 64 for every ViT the path covers (Tiny/Base/Large).
+ * ---------------------------------------------------------------------------------------- */
+int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtype,
+                     int64_t batch, int64_t tokens, int64_t heads, float scale, void* stream);
+int fv_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                     float* delta, void* dqkv, int dtype,
+                     int64_t batch, int64_t tokens, int64_t heads, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Patch embedding helpers (timm PatchEmbed.proj = Conv2d(C,D,16,16) + cls/pos, model.py:193).
+ *   fv_patchify: NCHW fp32 image -> [B*(H/16)*(W/16), C*256] rows in (c,py,px) order, bf16/fp32
+ *   fv_cls_pos_rows: writes row 0 of every image: x[b,0,:] = cls + pos[0]
+ * ---------------------------------------------------------------------------------------- */
+int fv_patchify(const float* img, void* out, int out_dtype,
+                int64_t batch, int64_t chans, int64_t height, int64_t width, void* stream);
+int fv_cls_pos_rows(const float* cls, const float* pos, float* x,
+                    int64_t batch, int64_t tokens, int64_t dim, void* stream);
+
+/* column sums: out[n] (+)= sum_m a[m,n]   (bias gradients, pos_embed / cls_token gradients)   */
+int fv_colsum(const void* a, int a_dtype, int64_t lda, float* out, int accumulate,
+              int64_t rows, int64_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses. fv_asl_loss replaces AsymmetricFocalLoss.forward (losses.py:41-67) AND its autograd
+ * backward in one pass; fv_ce_loss replaces F.cross_entropy (utils.py:262).
+ *   logits fp32 [B,C] (C <= 32), targets int64 [B]
+ *   loss   fp32 [1]  (mean over B; written, not accumulated)
+ *   dlogits fp32 [B,C] = d loss / d logits (may be NULL)
+ * ---------------------------------------------------------------------------------------- */
+int fv_asl_loss(const float* logits, const int64_t* targets, float* loss, float* dlogits,
+                int64_t batch, int64_t classes, float gamma_neg, float gamma_pos, float clip,
+                float eps, void* stream);
+int fv_ce_loss(const float* logits, const int64_t* targets, float* loss, float* dlogits,
+               int64_t batch, int64_t classes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser sweep over one flat fp32 parameter arena.
+ * Replaces clip_grad_norm_ (utils.py:192-193), torch.optim.AdamW.step over the LLRD groups
+ * (train.py:158,253-261; model.py:228-270), EMA.update (utils.py:76-83) and the bf16 re-cast
+ * of the weights, in one pass.
+ *   seg_end  : int64 [nseg] exclusive end offset of each segment (ascending, last == n)
+ *   seg_lr/seg_wd : fp32 [nseg] per-segment learning rate / weight decay; lr < 0 marks a
+ *              segment that is not optimised (cls_token / pos_embed quirk, model.py:228-270)
+ *   sumsq    : fp32 [1] device scalar, sum of squares of ALL gradients (fv_sumsq)
+ *   max_norm : clip threshold (<=0 disables); coefficient = min(1, max_norm/(sqrt(sumsq)+1e-6))
+ *   step     : 1-based step count for bias correction
+ *   ema/ema_decay : optional shadow arena (NULL to skip)
+ *   p_lp     : optional bf16 copy of the updated parameters (NULL to skip)
+ * ---------------------------------------------------------------------------------------- */
+int fv_sumsq(const float* g, int64_t n, float* sumsq, int accumulate, void* stream);
+int fv_adamw_flat(float* p, const float* g, float* m, float* v,
+                  const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int nseg,
+                  const float* sumsq, float max_norm, float beta1, float beta2, float eps,
+                  int64_t step, float* ema, float ema_decay, void* p_lp,
+                  int64_t n, void* stream);
+int fv_scale_inplace(float* x, const float* sumsq, float max_norm, int64_t n, void* stream);
+int fv_ema_update(float* shadow, const float* p, float decay, int64_t n, void* stream);
+int fv_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FedAvg local fold: acc = (init ? 0 : acc) + weight * w over a flat fp32 arena.
+ * There is no FedAvg in the reference; spec in SURVEY.md §8.2:
+ *   w_global = sum_k (n_k / sum_j n_j) * w_k, summed in client order in fp32.
+ * The cross-GPU sum is an NCCL allreduce issued by the host (torch.distributed).
+ * ---------------------------------------------------------------------------------------- */
+int fv_fedavg_accum(float* acc, const float* w, float weight, int init, int64_t n, void* stream);
+
+/* fp32 attention helpers for the parity path: row softmax fwd/bwd on [rows, cols] scores      */
+int fv_softmax_rows(const float* s, float* p, int64_t rows, int64_t cols, float scale, void* stream);
+int fv_softmax_rows_bwd(const float* p, const float* dp, float* ds, int64_t rows, int64_t cols,
+                        float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEDVIT_H_ */
