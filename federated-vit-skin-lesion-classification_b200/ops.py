@@ -50,24 +50,12 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------
-@torch.library.custom_op("fedvit::gemm", mutates_args=("out", "aux"))
-def gemm(
-    a: Tensor,
-    b: Tensor,
-    bias: Optional[Tensor],
-    out: Tensor,
-    aux: Optional[Tensor],
-    a_major: int,
-    b_major: int,
-    epilogue: int,
-    split_k: int,
-    tokens_per_img: int,
-) -> None:
-    """out[M,N] = op(a)[M,K] @ op(b)[N,K]^T with a fused epilogue (see include/fedvit.h).
+# bench.py's roofline leg: when set to a list, every tensor-core GEMM launch is bracketed by CUDA
+# events on its own stream and (start, end, algorithmic flops) is appended here.
+GEMM_TRACE: Optional[list] = None
 
-    ``a_major`` / ``b_major``: 0 = the operand is stored [rows, K]; 1 = stored [K, rows].
-    bf16 operands run on tcgen05 tensor cores, fp32 operands on the FFMA parity kernel.
-    """
+
+def _gemm_impl(a, b, bias, out, aux, a_major, b_major, epilogue, split_k, tokens_per_img) -> None:
     _need_cuda(a, b, bias, out, aux)
     if a.dim() != 2 or b.dim() != 2 or out.dim() != 2:
         raise FedVitError("gemm: operands must be 2-D")
@@ -88,11 +76,19 @@ def gemm(
     if a.dtype == torch.bfloat16:
         if b.dtype != torch.bfloat16:
             raise FedVitError("gemm: mixed operand dtypes")
+        trace = GEMM_TRACE
+        if trace is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         LIB.call(
             "fv_gemm_bf16", a.data_ptr(), a_major, a.stride(0), b.data_ptr(), b_major, b.stride(0),
             _ptr(bias), out.data_ptr(), _dt(out), out.stride(0), _ptr(aux), ldaux, m, n, k,
             epilogue, split_k, tokens_per_img, _stream(a),
         )
+        if trace is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            trace.append((e0, e1, 2.0 * m * n * k))
     else:
         if a.dtype != torch.float32 or b.dtype != torch.float32 or out.dtype != torch.float32:
             raise FedVitError("gemm: fp32 path needs fp32 a, b, out")
@@ -103,6 +99,37 @@ def gemm(
             out.data_ptr(), out.stride(0), 0, _ptr(aux), ldaux, m, n, k, 1, 1.0, epilogue,
             tokens_per_img, _stream(a),
         )
+
+
+@torch.library.custom_op("fedvit::gemm", mutates_args=("out",))
+def gemm(
+    a: Tensor,
+    b: Tensor,
+    bias: Optional[Tensor],
+    out: Tensor,
+    aux: Optional[Tensor],
+    a_major: int,
+    b_major: int,
+    epilogue: int,
+    split_k: int,
+    tokens_per_img: int,
+) -> None:
+    """out[M,N] = op(a)[M,K] @ op(b)[N,K]^T with a fused epilogue (see include/fedvit.h).
+
+    ``a_major`` / ``b_major``: 0 = the operand is stored [rows, K]; 1 = stored [K, rows].
+    ``aux`` is read-only here (residual, saved pre-activation, pos_embed); the GELU epilogue, which
+    writes a second output, is ``gemm_gelu``. bf16 operands run on tcgen05 tensor cores, fp32
+    operands on the FFMA parity kernel.
+    """
+    if epilogue == EPI["gelu"]:
+        raise FedVitError("gemm: use gemm_gelu for the GELU epilogue")
+    _gemm_impl(a, b, bias, out, aux, a_major, b_major, epilogue, split_k, tokens_per_img)
+
+
+@torch.library.custom_op("fedvit::gemm_gelu", mutates_args=("out", "pre"))
+def gemm_gelu(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor, pre: Tensor) -> None:
+    """pre = a @ b^T + bias ; out = gelu_erf(pre)  (fc1 of the MLP; both kept for the backward)."""
+    _gemm_impl(a, b, bias, out, pre, MAJOR_K, MAJOR_K, EPI["gelu"], 1, 0)
 
 
 @torch.library.custom_op("fedvit::bgemm_f32", mutates_args=("out",))

@@ -1,0 +1,338 @@
+#!/usr/bin/env python3
+"""Federated client training on B200 — the reference's ``train.py`` step loop plus the FedAvg
+round loop the reference lacks.
+
+Kept from the reference (same names / signatures / config keys):
+    train_one_epoch(model, loader, criterion, optimizer, scheduler, scaler, ema, device, config,
+                    epoch, logger) -> float                         (reference train.py:95-168)
+    validate(model, loader, criterion, device, config) -> dict      (reference train.py:175-214)
+``train_one_epoch`` is one client's local epoch. Differences, all below the seam:
+  * mixed precision is bf16 (``training.amp_dtype``), so the GradScaler is an identity
+    (reference: fp16 + GradScaler, train.py:144,270) — a deliberate divergence asked for by the
+    baseline configuration;
+  * the per-step ``loss.item()`` host sync (train.py:164) is gone: the running loss is
+    accumulated on the device and read once per epoch;
+  * clip + AdamW + EMA are one kernel sweep (optim.FusedAdamW).
+
+Added (the reference has no federated code): ``run_federated`` — the round loop
+shaped like the reference's epoch loop (train.py:281-319): every round each client restarts from
+the global weights, trains ``local_epochs`` epochs on its shard, is folded into the weighted
+accumulator; one NCCL allreduce; scheduler stepped once per round.
+
+    python -m fedvit_b200.train --config config.yaml                       # 1 GPU
+    torchrun --nproc-per-node 8 -m fedvit_b200.train --config config.yaml  # clients over 8 GPUs
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import os
+import sys
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .arena import FlatArena
+from .data import SyntheticClientLoader, client_label_probs, client_sizes
+from .fedavg import FedAvgAggregator, broadcast_initial, clients_of_rank, dist_info
+from .losses import build_loss
+from .model import build_model, count_parameters, get_layerwise_lr_groups
+from .optim import FusedAdamW
+from .utils import EMA, WarmupCosineScheduler, clip_grad_norm, get_device, load_config, seed_everything
+
+
+def setup_logging(log_dir: Optional[str] = None, tag: str = "fed") -> logging.Logger:
+    logger = logging.getLogger(f"fedvit_{tag}")
+    logger.setLevel(logging.INFO)
+    if not logger.handlers:  # (the reference re-adds handlers on every call; once is enough)
+        h = logging.StreamHandler(sys.stdout)
+        h.setFormatter(logging.Formatter("%(asctime)s | %(message)s", datefmt="%H:%M:%S"))
+        logger.addHandler(h)
+        if log_dir:
+            os.makedirs(log_dir, exist_ok=True)
+            fh = logging.FileHandler(os.path.join(log_dir, f"train_{tag}.log"))
+            fh.setFormatter(logging.Formatter("%(asctime)s | %(message)s"))
+            logger.addHandler(fh)
+    return logger
+
+
+def _amp_settings(config: dict, device: torch.device):
+    t = config.get("training", {})
+    use_amp = bool(t.get("use_amp", True)) and device.type == "cuda"
+    name = str(t.get("amp_dtype", "bf16")).lower()
+    if name not in ("bf16", "bfloat16"):
+        raise ValueError("training.amp_dtype: only bf16 is implemented on the B200 path")
+    return use_amp, torch.bfloat16
+
+
+def _device_batches(loader, device: torch.device):
+    """Yield the loader's batches on ``device`` with a one-batch look-ahead: the next batch's
+    host->device copies run on a side stream while the current step computes (the reference issues
+    them on the compute stream, train.py:132-136). Batches already on the device pass through."""
+    if device.type != "cuda":
+        raise RuntimeError("this path trains on CUDA only")
+    copy_stream = torch.cuda.Stream(device)
+
+    def stage(batch):
+        with torch.cuda.stream(copy_stream):
+            moved = {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        return moved, ev
+
+    it = iter(loader)
+    try:
+        nxt = stage(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        cur, ev = nxt
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            nxt = None
+        main = torch.cuda.current_stream(device)
+        main.wait_event(ev)
+        for v in cur.values():
+            if torch.is_tensor(v):
+                v.record_stream(main)
+        yield cur
+
+
+# ================================================================================================
+# one client's local epoch
+# ================================================================================================
+def train_one_epoch(model: nn.Module, loader, criterion, optimizer, scheduler, scaler, ema: Optional[EMA],
+                    device: torch.device, config: dict, epoch: int, logger: Optional[logging.Logger]) -> float:
+    model.train()
+    t = config.get("training", {})
+    use_amp, amp_dtype = _amp_settings(config, device)
+    grad_clip = t.get("grad_clip", 1.0)
+    accum = max(1, int(t.get("gradient_accumulation_steps", 1)))
+    use_meta = config.get("model", {}).get("metadata", {}).get("enabled", True)
+    aug = config.get("augmentation", {})
+    if aug.get("mixup", {}).get("alpha", 0.0) > 0 or aug.get("cutmix", {}).get("prob", 0.0) > 0:
+        raise NotImplementedError("MixUp/CutMix are host-side augmentation outside this path "
+                                  "(SURVEY.md §2); set augmentation.mixup.alpha: 0 and cutmix.prob: 0")
+
+    loss_sum = torch.zeros((), device=device, dtype=torch.float32)
+    seen = 0
+    n_steps = len(loader)
+    optimizer.zero_grad(set_to_none=True)
+    sync_every_step = bool(t.get("sync_loss_every_step", False))  # the reference's per-step .item()
+    host_loss = 0.0
+    for step, batch in enumerate(_device_batches(loader, device)):
+        images, labels, meta = batch["image"], batch["label"], batch.get("metadata")
+        bs = images.size(0)
+
+        with torch.amp.autocast(device_type=device.type, enabled=use_amp, dtype=amp_dtype):
+            logits = model(images, metadata=meta if use_meta else None)["logits"]
+            loss = criterion(logits, labels) / accum
+
+        if scaler is not None:
+            scaler.scale(loss).backward()
+        else:
+            loss.backward()
+
+        if (step + 1) % accum == 0 or (step + 1) == n_steps:
+            if scaler is not None and scaler.is_enabled():
+                scaler.unscale_(optimizer)
+                clip_grad_norm(model.parameters(), grad_clip)
+                scaler.step(optimizer)
+                scaler.update()
+            else:
+                clip_grad_norm(model.parameters(), grad_clip, optimizer=optimizer)
+                optimizer.step()
+            optimizer.zero_grad(set_to_none=True)
+            if ema is not None:
+                ema.update()
+
+        if sync_every_step:
+            host_loss += float(loss.item()) * accum * bs
+        else:
+            loss_sum += loss.detach() * (accum * bs)
+        seen += bs
+    if sync_every_step:
+        return host_loss / max(seen, 1)
+    return float(loss_sum.item()) / max(seen, 1)
+
+
+# ================================================================================================
+# validation
+# ================================================================================================
+def classification_metrics(labels: np.ndarray, preds: np.ndarray, num_classes: int) -> Dict[str, float]:
+    """accuracy / balanced accuracy / macro-F1 with sklearn's conventions (mean recall over the
+    classes present in ``labels``; F1 averaged over classes present in labels or predictions,
+    zero_division=0) — what reference train.py:211-213 reports."""
+    cm = np.zeros((num_classes, num_classes), dtype=np.int64)
+    np.add.at(cm, (labels, preds), 1)
+    tp = np.diag(cm).astype(np.float64)
+    support, predicted = cm.sum(1).astype(np.float64), cm.sum(0).astype(np.float64)
+    present = support > 0
+    recall = np.divide(tp, support, out=np.zeros_like(tp), where=present)
+    precision = np.divide(tp, predicted, out=np.zeros_like(tp), where=predicted > 0)
+    denom = precision + recall
+    f1 = np.divide(2 * precision * recall, denom, out=np.zeros_like(tp), where=denom > 0)
+    used = present | (predicted > 0)
+    return {
+        "accuracy": float(tp.sum() / max(cm.sum(), 1)),
+        "balanced_accuracy": float(recall[present].mean()) if present.any() else 0.0,
+        "macro_f1": float(f1[used].mean()) if used.any() else 0.0,
+    }
+
+
+@torch.no_grad()
+def validate(model: nn.Module, loader, criterion, device: torch.device, config: dict) -> dict:
+    model.eval()
+    use_amp, amp_dtype = _amp_settings(config, device)
+    use_meta = config.get("model", {}).get("metadata", {}).get("enabled", True)
+    loss_sum = torch.zeros((), device=device, dtype=torch.float32)
+    seen = 0
+    preds: List[torch.Tensor] = []
+    gold: List[torch.Tensor] = []
+    for batch in _device_batches(loader, device):
+        images, labels, meta = batch["image"], batch["label"], batch.get("metadata")
+        with torch.amp.autocast(device_type=device.type, enabled=use_amp, dtype=amp_dtype):
+            logits = model(images, metadata=meta if use_meta else None)["logits"]
+            loss = criterion(logits, labels)
+        bs = images.size(0)
+        loss_sum += loss * bs
+        seen += bs
+        preds.append(logits.argmax(1))
+        gold.append(labels)
+    p = torch.cat(preds).cpu().numpy()
+    y = torch.cat(gold).cpu().numpy()
+    out = {"loss": float(loss_sum.item()) / max(seen, 1)}
+    out.update(classification_metrics(y, p, int(config.get("model", {}).get("num_classes", 8))))
+    return out
+
+
+# ================================================================================================
+# FedAvg round loop
+# ================================================================================================
+def build_client_loaders(config: dict, client_ids: List[int], device_resident: bool, device) -> Dict[int, SyntheticClientLoader]:
+    fed = config.get("federated", {})
+    m = config.get("model", {})
+    t = config.get("training", {})
+    sizes = client_sizes(config)
+    k = len(sizes)
+    probs = client_label_probs(k, int(m.get("num_classes", 8)), fed.get("partition", "iid"),
+                               float(fed.get("dirichlet_alpha", 0.5)), int(config.get("seed", 42)))
+    meta_on = m.get("metadata", {}).get("enabled", True)
+    ch = 4 if config.get("data", {}).get("use_segmentation_mask", False) else 3
+    return {
+        c: SyntheticClientLoader(
+            c, sizes[c], int(t.get("batch_size", 16)), int(m.get("image_size", 384)), ch,
+            int(m.get("num_classes", 8)), None if fed.get("partition", "iid") == "iid" else probs[c],
+            int(m.get("metadata", {}).get("input_dim", 13)) if meta_on else 0,
+            pool=fed.get("synthetic_pool"), device=device if device_resident else None)
+        for c in client_ids
+    }
+
+
+def run_federated(config: dict, device: Optional[torch.device] = None, logger: Optional[logging.Logger] = None,
+                  loaders: Optional[Dict[int, SyntheticClientLoader]] = None, val_loader=None,
+                  device_resident: bool = False) -> dict:
+    """FedAvg over ``federated.num_clients`` clients for ``federated.rounds`` rounds. Returns the
+    per-round records (wall time from CUDA events, images/s, mean client loss, allreduce time)."""
+    fed = config.get("federated", {})
+    t = config.get("training", {})
+    rank, world = dist_info()
+    device = device or get_device("auto")
+    logger = logger or setup_logging(tag=f"r{rank}")
+    seed_everything(int(config.get("seed", 42)))
+
+    model = build_model(config).to(device)
+    arena = FlatArena(model)
+    broadcast_initial(arena, model)
+    opt_cfg, llrd = t.get("optimizer", {}), t.get("llrd", {})
+    groups = get_layerwise_lr_groups(
+        model, base_lr=opt_cfg.get("lr", 1e-4),
+        decay_rate=llrd.get("decay_rate", 0.75) if llrd.get("enabled", True) else 1.0,
+        weight_decay=opt_cfg.get("weight_decay", 1e-5))
+    optimizer = FusedAdamW(groups, weight_decay=opt_cfg.get("weight_decay", 1e-5), arena=arena)
+    rounds = int(fed.get("rounds", 1))
+    sched_cfg = t.get("scheduler", {})
+    scheduler = WarmupCosineScheduler(optimizer, warmup_epochs=sched_cfg.get("warmup_epochs", 0),
+                                      total_epochs=max(rounds, 1), min_lr=sched_cfg.get("min_lr", 1e-6))
+    ema_cfg = t.get("ema", {})
+    ema = EMA(model, decay=ema_cfg.get("decay", 0.9995)).attach(optimizer) if ema_cfg.get("enabled", False) else None
+    scaler = torch.amp.GradScaler(device.type, enabled=False)  # bf16: no loss scaling
+    criterion = build_loss(config).to(device)
+
+    sizes = client_sizes(config)
+    n_total = sum(sizes)
+    mine = clients_of_rank(len(sizes), rank, world)
+    if loaders is None:
+        loaders = build_client_loaders(config, mine, device_resident, device)
+    agg = FedAvgAggregator(model, arena)
+    local_epochs = int(fed.get("local_epochs", 1))
+    if rank == 0:
+        logger.info(f"FedAvg: {len(sizes)} clients over {world} GPU(s), {rounds} rounds x {local_epochs} "
+                    f"local epoch(s); params {count_parameters(model):,}; clients of rank 0: {mine}")
+
+    records = []
+    for rnd in range(1, rounds + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        ev[0].record()
+        agg.begin_round()
+        losses = []
+        for c in mine:
+            agg.load_global()
+            optimizer.reset_state()  # canonical FedAvg: client optimiser state does not survive the round
+            for e in range(local_epochs):
+                losses.append(train_one_epoch(model, loaders[c], criterion, optimizer, scheduler, scaler,
+                                              ema, device, config, e + 1, logger))
+            agg.fold(sizes[c], n_total, client_id=c)
+        ev[1].record()
+        agg.finish()
+        ev[2].record()
+        torch.cuda.synchronize(device)
+        scheduler.step()
+        ms = torch.tensor([ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[2])], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        images = n_total * local_epochs  # all ranks together (drop_last: whole batches only)
+        images = sum((s // int(t.get("batch_size", 16))) * int(t.get("batch_size", 16)) for s in sizes) * local_epochs
+        rec = {"round": rnd, "round_ms": float(ms[0]), "aggregate_ms": float(ms[1]),
+               "images_per_s": images / (float(ms[0]) / 1e3), "mean_client_loss": float(np.mean(losses)) if losses else None}
+        if val_loader is not None:
+            if ema is not None:
+                ema.apply_shadow()
+            rec["val"] = validate(model, val_loader, criterion, device, config)
+            if ema is not None:
+                ema.restore()
+        records.append(rec)
+        if rank == 0:
+            logger.info(f"  round {rnd:02d} | {rec['round_ms']:.1f} ms | {rec['images_per_s']:.0f} img/s | "
+                        f"aggregate {rec['aggregate_ms']:.2f} ms | loss {rec['mean_client_loss']}")
+    return {"rounds": records, "model": model, "arena": arena}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser(description="FedAvg ViT client training on B200 (synthetic shards)")
+    ap.add_argument("--config", type=str, default=os.path.join(os.path.dirname(__file__), "config.yaml"))
+    ap.add_argument("--log", type=str, default=None)
+    ap.add_argument("--seed", type=int, default=None)
+    args = ap.parse_args()
+    config = load_config(args.config)
+    if args.seed is not None:
+        config["seed"] = args.seed
+    if "RANK" in os.environ and not dist.is_initialized():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    rank, _ = dist_info()
+    run_federated(config, logger=setup_logging(args.log, tag=f"r{rank}"))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+"""Training utilities of the path — the reference's ``utils.py`` names that ``train.py`` imports
+for it (EMA, clip_grad_norm, WarmupCosineScheduler, seed_everything, get_device, load_config,
+checkpoint save/load), re-implemented over the flat arena.
+
+Out of scope here: MixUp/CutMix, TTA evaluation, auto batch-size probing, the
+sklearn metric tables — they are host-side data/driver code, not the hot path.
+"""
+from __future__ import annotations
+
+import math
+import os
+import random
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.optim.lr_scheduler import LRScheduler
+
+from . import ops
+from .arena import FlatArena, arena_of
+
+
+def seed_everything(seed: int = 42) -> None:
+    """Seeds python / numpy / torch (reference utils.py:25-33)."""
+    os.environ["PYTHONHASHSEED"] = str(seed)
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def get_device(device_str: str = "auto") -> torch.device:
+    """CUDA only: the MPS / CPU branches of reference utils.py:36-43 are out of scope by design."""
+    if device_str in ("auto", "cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("fedvit_b200 needs a CUDA (sm_100a) device; no MPS/CPU fallback on this path")
+        return torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device_str)
+    if dev.type != "cuda":
+        raise RuntimeError(f"device {device_str!r} is not supported: CUDA (sm_100a) only")
+    return dev
+
+
+def load_config(path: str) -> dict:
+    import yaml
+
+    with open(path) as f:
+        return yaml.safe_load(f)
+
+
+# ----------------------------------------------------------------------------------------------
+# EMA
+# ----------------------------------------------------------------------------------------------
+class EMA:
+    """Exponential moving average of the trainable parameters — API of reference utils.py:50-105
+    (``update`` / ``apply_shadow`` / ``restore`` / ``state_dict`` / ``load_state_dict``).
+
+    The shadow is ONE flat fp32 buffer mirroring the parameter arena, so ``update`` is a single
+    HBM sweep (12 B/param) instead of a Python loop of ~2x150 launches — or no extra sweep at all
+    once attached to a ``FusedAdamW`` (``attach``), which folds it into the optimiser kernel.
+    ``apply_shadow`` / ``restore`` are two flat copies."""
+
+    def __init__(self, model: nn.Module, decay: float = 0.9995) -> None:
+        self.model = model
+        self.decay = decay
+        arena = arena_of(model)
+        if arena is None:
+            arena = FlatArena(model)
+        self.arena = arena
+        self.flat = arena.params.clone()
+        self._backup: Optional[torch.Tensor] = None
+        self._fused_updates = 0
+        self._seen_fused = 0
+
+    def attach(self, optimizer) -> "EMA":
+        optimizer.ema = self
+        return self
+
+    @torch.no_grad()
+    def update(self) -> None:
+        if self._fused_updates > self._seen_fused:  # the optimiser sweep already did this step's update
+            self._seen_fused = self._fused_updates
+            return
+        ops.ema_update(self.flat, self.arena.params, self.decay)
+
+    @torch.no_grad()
+    def apply_shadow(self) -> None:
+        self._backup = self.arena.params.clone()
+        self.arena.params.copy_(self.flat)
+        self._touch()
+
+    @torch.no_grad()
+    def restore(self) -> None:
+        if self._backup is not None:
+            self.arena.params.copy_(self._backup)
+            self._backup = None
+            self._touch()
+
+    def _touch(self) -> None:
+        if self.arena.lp is not None:
+            self.arena.refresh_lp(force=True)
+
+    @property
+    def shadow(self) -> Dict[str, torch.Tensor]:
+        return {n: self.arena.view(self.flat, n) for n, p in zip(self.arena.names, self.arena._params)
+                if p.requires_grad}
+
+    def state_dict(self) -> dict:
+        return {"shadow": {k: v.detach().cpu().clone() for k, v in self.shadow.items()}, "decay": self.decay}
+
+    def load_state_dict(self, sd: dict) -> None:
+        for k, v in sd["shadow"].items():
+            self.arena.view(self.flat, k).copy_(v)
+        self.decay = sd.get("decay", self.decay)
+
+
+# ----------------------------------------------------------------------------------------------
+# schedule, clipping
+# ----------------------------------------------------------------------------------------------
+class WarmupCosineScheduler(LRScheduler):
+    """Linear warm-up over ``warmup_epochs`` then cosine decay to ``min_lr``; stepped once per
+    epoch — per FedAvg round in the federated loop (reference utils.py:171-185, train.py:297)."""
+
+    def __init__(self, optimizer, warmup_epochs: int, total_epochs: int, min_lr: float = 1e-6,
+                 last_epoch: int = -1) -> None:
+        self.warmup_epochs = warmup_epochs
+        self.total_epochs = total_epochs
+        self.min_lr = min_lr
+        super().__init__(optimizer, last_epoch)
+
+    def get_lr(self):
+        e = self.last_epoch
+        if e < self.warmup_epochs:
+            f = e / max(1, self.warmup_epochs)
+            return [b * f for b in self.base_lrs]
+        t = (e - self.warmup_epochs) / max(1, self.total_epochs - self.warmup_epochs)
+        c = 0.5 * (1.0 + math.cos(math.pi * t))
+        return [self.min_lr + (b - self.min_lr) * c for b in self.base_lrs]
+
+
+def clip_grad_norm(parameters: Iterable[nn.Parameter], max_norm: float = 1.0, optimizer=None) -> torch.Tensor:
+    """Global L2 norm over ALL given gradients (incl. the never-stepped cls_token / pos_embed, as
+    in the reference: utils.py:192-193 on ``model.parameters()``, train.py:157) and clipping by
+    ``min(1, max_norm / (norm + 1e-6))``. Returns the norm as a device scalar (no host sync).
+
+    With a ``FusedAdamW`` passed as ``optimizer`` the rescale is not a pass of its own: the
+    coefficient is applied when the optimiser sweep reads the gradients."""
+    params = [p for p in parameters if p.grad is not None]
+    if not params:
+        return torch.zeros(())
+    arena = getattr(params[0], "_fv_arena", (None,))[0]
+    in_arena = arena is not None and all(
+        getattr(p, "_fv_arena", (None,))[0] is arena and p.grad.data_ptr() == arena.grad_view(p).data_ptr()
+        for p in params)
+    if in_arena and len(params) == sum(1 for q in arena._params if q.grad is not None):
+        sumsq = torch.zeros(1, device=arena.device, dtype=torch.float32)
+        ops.sumsq(arena.grads, sumsq, False)
+        if optimizer is not None and hasattr(optimizer, "defer_clip"):
+            optimizer.defer_clip(sumsq, max_norm)
+        else:
+            ops.scale_by_clip(arena.grads, sumsq, float(max_norm))
+        return sumsq.sqrt().squeeze(0)
+    # gradients living outside one arena: per-tensor sums of squares into one device scalar
+    dev = params[0].grad.device
+    sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+    flats = []
+    for p in params:
+        g = p.grad.contiguous().view(-1)
+        if g.numel() % 4 or g.data_ptr() % 16:
+            pad = torch.zeros((g.numel() + 3) // 4 * 4, device=dev, dtype=torch.float32)
+            pad[: g.numel()] = g
+            g = pad
+        flats.append((p, g))
+        ops.sumsq(g, sumsq, True)
+    coef = (max_norm / (sumsq.sqrt() + 1e-6)).clamp(max=1.0)
+    for p, _ in flats:
+        p.grad.mul_(coef.to(p.grad.dtype))
+    return sumsq.sqrt().squeeze(0)
+
+
+# ----------------------------------------------------------------------------------------------
+# checkpoint (same dict layout as reference utils.py:287-308, so files interchange)
+# ----------------------------------------------------------------------------------------------
+def save_checkpoint(model, optimizer, scheduler, ema, epoch, metric, path, config=None) -> None:
+    torch.save({
+        "epoch": epoch,
+        "model_state_dict": model.state_dict(),
+        "optimizer_state_dict": optimizer.state_dict() if optimizer else None,
+        "scheduler_state_dict": scheduler.state_dict() if scheduler else None,
+        "ema_state_dict": ema.state_dict() if ema else None,
+        "best_metric": metric,
+        "config": config,
+    }, path)
+
+
+def load_checkpoint(path, model, optimizer=None, scheduler=None, ema=None, device=None):
+    ckpt = torch.load(path, map_location=device or "cpu", weights_only=False)
+    model.load_state_dict(ckpt["model_state_dict"])
+    if optimizer and ckpt.get("optimizer_state_dict"):
+        optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+    if scheduler and ckpt.get("scheduler_state_dict"):
+        scheduler.load_state_dict(ckpt["scheduler_state_dict"])
+    if ema and ckpt.get("ema_state_dict"):
+        ema.load_state_dict(ckpt["ema_state_dict"])
+    return ckpt

@@ -1,0 +1,422 @@
+"""timm-compatible ``VisionTransformer`` whose forward AND backward run on the libfedvit kernels.
+
+This is the object the reference obtains from ``timm.create_model(...)`` at model.py:112-117 and
+calls at model.py:193. It keeps everything model.py touches: ``num_features``,
+a re-assignable ``patch_embed.proj`` (``nn.Conv2d``), iterable ``blocks``, ``norm``, and timm's
+state_dict keys — so checkpoints interchange and ``_modify_input_channels`` /
+``get_layerwise_lr_groups`` work unchanged.
+
+The ``nn.Linear`` / ``nn.LayerNorm`` / ``nn.Conv2d`` children are *parameter holders only*; their
+own forwards are never called. ``forward`` is one ``torch.autograd.Function`` over the whole
+backbone with a hand-written backward:
+
+  forward  per block: LN -> qkv GEMM(+bias) -> flash attention -> proj GEMM(+bias+residual)
+                      -> LN -> fc1 GEMM(+bias, GELU, keeps pre-activation) -> fc2 GEMM(+bias+residual)
+  backward per block: dgrad GEMMs (fc2's fused with GELU'), wgrad GEMMs (split-K, accumulate into
+                      the fp32 gradient arena), column-sum bias grads, fused LN backward that also
+                      adds the residual-path gradient and emits the bf16 copy the next GEMM reads.
+
+Arithmetic modes (chosen per call, like the reference's ``torch.amp.autocast`` at train.py:144):
+  * autocast active  -> bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 residual
+    stream / LN statistics / softmax (SURVEY.md Appendix B semantics);
+  * otherwise        -> fp32 everywhere (FFMA GEMM kernel) — the 1e-4 parity configuration.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+from ._lib import FedVitError
+
+_K, _MN = ops.MAJOR_K, ops.MAJOR_MN
+_E = ops.EPI
+
+_ARCH = {
+    "vit_micro": (64, 2, 1),  # test-only toy size (matches oracle/timm)
+    "vit_tiny": (192, 12, 3),
+    "vit_small": (384, 12, 6),
+    "vit_base": (768, 12, 12),
+    "vit_large": (1024, 24, 16),
+}
+
+
+def parse_vit_name(name: str) -> Tuple[int, int, int, int, int]:
+    """'vit_base_patch16_224.augreg_in21k' -> (embed_dim, depth, heads, patch, img)."""
+    parts = name.split(".")[0].split("_")
+    if len(parts) != 4 or parts[0] != "vit" or not parts[2].startswith("patch"):
+        raise ValueError(
+            f"{name!r}: this path covers timm ViT names 'vit_<size>_patch16_<img>' "
+            f"(sizes: {sorted(_ARCH)}); other backbones (e.g. SwinV2) are out of scope"
+        )
+    arch = "_".join(parts[:2])
+    if arch not in _ARCH:
+        raise ValueError(f"unknown ViT size in {name!r}; known: {sorted(_ARCH)}")
+    patch, img = int(parts[2][5:]), int(parts[3])
+    if patch != 16:
+        raise ValueError("only patch16 ViTs are covered")
+    if img % 16:
+        raise ValueError("image size must be a multiple of 16")
+    return (*_ARCH[arch], patch, img)
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter holders with timm's attribute / key names
+# ----------------------------------------------------------------------------------------------
+class PatchEmbed(nn.Module):
+    def __init__(self, img_size: int, patch_size: int, in_chans: int, embed_dim: int) -> None:
+        super().__init__()
+        self.img_size = (img_size, img_size)
+        self.patch_size = (patch_size, patch_size)
+        self.grid_size = (img_size // patch_size, img_size // patch_size)
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=True)
+
+
+class Attention(nn.Module):
+    def __init__(self, dim: int, num_heads: int) -> None:
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim, bias=True)
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim: int, hidden: int) -> None:
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden, bias=True)
+        self.fc2 = nn.Linear(hidden, dim, bias=True)
+
+
+class Block(nn.Module):
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float, drop_path: float) -> None:
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = Attention(dim, num_heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+        self.drop_path_rate = float(drop_path)
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+def _grad_buffer(p: nn.Parameter) -> Tensor:
+    """Where this parameter's gradient is accumulated. Creates (zeroed) ``p.grad`` on first use;
+    inside a FlatArena that is the parameter's slice of the flat gradient buffer."""
+    if p.grad is None:
+        a = getattr(p, "_fv_arena", None)
+        if a is not None and a[0].owns(p):
+            g = a[0].grad_view(p)
+            g.zero_()
+            p.grad = g
+        else:
+            p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+def _split_k_for(out_rows: int, out_cols: int, k: int) -> int:
+    """Enough K slices that a weight-gradient GEMM (tiny M x N, huge K = tokens) fills 148 SMs."""
+    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
+    kb = (k + 63) // 64
+    want = max(1, 148 // max(tiles, 1))
+    return max(1, min(want, max(1, kb // 8)))
+
+
+def _to_bf16(t: Tensor) -> Tensor:
+    t = t.contiguous()
+    out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    ops.cast_bf16(t, out)
+    return out
+
+
+class _Saved:
+    __slots__ = ("lp", "B", "N", "img_shape", "patches", "blocks", "cls_rows", "meanf", "rstdf")
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, img_size: int = 224, patch_size: int = 16, in_chans: int = 3,
+                 num_classes: int = 0, embed_dim: int = 768, depth: int = 12, num_heads: int = 12,
+                 mlp_ratio: float = 4.0, drop_path_rate: float = 0.0) -> None:
+        super().__init__()
+        if embed_dim // num_heads != 64:
+            raise ValueError("head_dim must be 64 (true for every timm ViT size)")
+        if num_classes != 0:
+            raise ValueError("the reference builds the backbone with num_classes=0 (model.py:115)")
+        self.num_classes = 0
+        self.num_features = self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.num_prefix_tokens = 1
+        self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim)
+        self.num_tokens = self.patch_embed.num_patches + 1
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.num_tokens, embed_dim))
+        dpr = [r.item() for r in torch.linspace(0, drop_path_rate, depth)]
+        self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio, dpr[i]) for i in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.init_weights()
+
+    def init_weights(self) -> None:
+        # timm's init for pretrained=False: trunc_normal(.02) Linear weights and
+        # pos_embed, zero biases, cls_token ~ N(0, 1e-6); the patch conv keeps PyTorch's default.
+        nn.init.trunc_normal_(self.pos_embed, std=0.02, a=-2.0, b=2.0)
+        nn.init.normal_(self.cls_token, std=1e-6)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02, a=-2.0, b=2.0)
+                nn.init.zeros_(m.bias)
+
+    # ------------------------------------------------------------------------------------------
+    def _bb_params(self) -> List[nn.Parameter]:
+        return list(self.parameters())
+
+    def _w(self, p: nn.Parameter, lp: bool) -> Tensor:
+        """GEMM operand for a weight: the fp32 master (fp32 mode) or its bf16 shadow."""
+        w = p.detach()
+        if w.dim() == 4:
+            w = w.reshape(w.shape[0], -1)
+        if not lp:
+            return w
+        a = getattr(p, "_fv_arena", None)
+        if a is not None and a[0].lp is not None and a[0].owns(p):
+            v = a[0].lp_view(p)
+            return v.reshape(v.shape[0], -1) if v.dim() == 4 else v
+        return _to_bf16(w)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise FedVitError(
+                "fedvit_b200 backbone runs on CUDA (sm_100a) only — no CPU/MPS fallback on this path"
+            )
+        pe = self.patch_embed
+        if tuple(x.shape[-2:]) != pe.img_size:
+            raise ValueError(f"input {tuple(x.shape[-2:])} != model image size {pe.img_size}")
+        if x.shape[1] != pe.proj.weight.shape[1]:
+            raise ValueError(f"input has {x.shape[1]} channels, patch_embed.proj expects {pe.proj.weight.shape[1]}")
+        if self.training and any(b.drop_path_rate > 0 for b in self.blocks):
+            raise NotImplementedError(
+                "stochastic depth (drop_path_rate > 0) is not on the B200 path yet; set "
+                "model.drop_path_rate: 0 (the parity / benchmark configurations do, SURVEY.md §8d)"
+            )
+        lp = torch.is_autocast_enabled("cuda")
+        if lp:
+            a = getattr(self.cls_token, "_fv_arena", None)
+            if a is not None and a[0].lp is not None and a[0].owns(self.cls_token):
+                a[0].refresh_lp()
+        params = self._bb_params()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad:
+            return _VitFunction.apply(self, x.float(), lp, *params)
+        feats, _ = self._forward_impl(x.float(), lp, save=False)
+        return feats
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def _attention_fwd(self, qkv: Tensor, B: int, N: int, lp: bool):
+        H, scale = self.num_heads, 64 ** -0.5
+        if lp:
+            o, lse = ops.attention_fwd(qkv, B, N, H, scale)
+            return o, lse
+        # fp32 parity path: S = Q K^T, P = softmax(scale S), O = P V as strided-batched FFMA GEMMs
+        D = H * 64
+        P = torch.empty((B, H, N, N), device=qkv.device, dtype=torch.float32)
+        o = torch.empty((B * N, D), device=qkv.device, dtype=torch.float32)
+        for h in range(H):
+            q, k, v = (qkv[:, s * D + h * 64:] for s in range(3))
+            ops.bgemm_f32(q, [3 * D, 1, N * 3 * D], k, [3 * D, 1, N * 3 * D], P[:, h], [N, H * N * N],
+                          N, N, 64, B, 1.0, False)
+        P = ops.softmax_rows(P, scale)
+        for h in range(H):
+            v = qkv[:, 2 * D + h * 64:]
+            ops.bgemm_f32(P[:, h], [N, 1, H * N * N], v, [1, 3 * D, N * 3 * D], o[:, h * 64:], [D, N * D],
+                          N, 64, N, B, 1.0, False)
+        return o, P
+
+    def _attention_bwd(self, qkv: Tensor, o: Tensor, do: Tensor, aux: Tensor, B: int, N: int, lp: bool) -> Tensor:
+        H, scale = self.num_heads, 64 ** -0.5
+        if lp:
+            return ops.attention_bwd(qkv, o, do, aux, B, N, H, scale)
+        D = H * 64
+        P = aux
+        dqkv = torch.empty_like(qkv)
+        dP = torch.empty_like(P)
+        for h in range(H):
+            v = qkv[:, 2 * D + h * 64:]
+            dO = do[:, h * 64:]
+            # dV[key,d] = sum_q P[q,key] dO[q,d]
+            ops.bgemm_f32(P[:, h], [1, N, H * N * N], dO, [1, D, N * D], dqkv[:, 2 * D + h * 64:],
+                          [3 * D, N * 3 * D], N, 64, N, B, 1.0, False)
+            # dP[q,key] = sum_d dO[q,d] V[key,d]
+            ops.bgemm_f32(dO, [D, 1, N * D], v, [3 * D, 1, N * 3 * D], dP[:, h], [N, H * N * N],
+                          N, N, 64, B, 1.0, False)
+        dS = ops.softmax_rows_bwd(P, dP, scale)
+        for h in range(H):
+            q, k = qkv[:, h * 64:], qkv[:, D + h * 64:]
+            # dQ[q,d] = sum_key dS[q,key] K[key,d]
+            ops.bgemm_f32(dS[:, h], [N, 1, H * N * N], k, [1, 3 * D, N * 3 * D], dqkv[:, h * 64:],
+                          [3 * D, N * 3 * D], N, 64, N, B, 1.0, False)
+            # dK[key,d] = sum_q dS[q,key] Q[q,d]
+            ops.bgemm_f32(dS[:, h], [1, N, H * N * N], q, [1, 3 * D, N * 3 * D], dqkv[:, D + h * 64:],
+                          [3 * D, N * 3 * D], N, 64, N, B, 1.0, False)
+        return dqkv
+
+    def _forward_impl(self, img: Tensor, lp: bool, save: bool):
+        B = img.shape[0]
+        N, D = self.num_tokens, self.embed_dim
+        M = B * N
+        dev = img.device
+        act = torch.bfloat16 if lp else torch.float32
+        pe = self.patch_embed
+
+        patches = ops.patchify(img, lp)  # [B*(N-1), C*256]
+        x = torch.empty((M, D), device=dev, dtype=torch.float32)
+        ops.gemm(patches, self._w(pe.proj.weight, lp), pe.proj.bias.detach(), x,
+                 self.pos_embed.detach().view(N, D), _K, _K, _E["patch"], 1, N - 1)
+        ops.cls_pos_rows(self.cls_token.detach(), self.pos_embed.detach(), x, B, N, D)
+
+        st = None
+        if save:
+            st = _Saved()
+            st.lp, st.B, st.N = lp, B, N
+            st.patches = patches
+            st.blocks = []
+        for blk in self.blocks:
+            n1, n2, at, mlp = blk.norm1, blk.norm2, blk.attn, blk.mlp
+            h, mean1, rstd1 = ops.layernorm_fwd(x, n1.weight.detach(), n1.bias.detach(), n1.eps, lp)
+            qkv = torch.empty((M, 3 * D), device=dev, dtype=act)
+            ops.gemm(h, self._w(at.qkv.weight, lp), at.qkv.bias.detach(), qkv, None, _K, _K, _E["none"], 1, 0)
+            o, aux = self._attention_fwd(qkv, B, N, lp)
+            x1 = torch.empty((M, D), device=dev, dtype=torch.float32)
+            ops.gemm(o, self._w(at.proj.weight, lp), at.proj.bias.detach(), x1, x, _K, _K, _E["residual"], 1, 0)
+            h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2.weight.detach(), n2.bias.detach(), n2.eps, lp)
+            hid = mlp.fc1.weight.shape[0]
+            u = torch.empty((M, hid), device=dev, dtype=act)
+            a = torch.empty((M, hid), device=dev, dtype=act)
+            ops.gemm_gelu(h2, self._w(mlp.fc1.weight, lp), mlp.fc1.bias.detach(), a, u)
+            x2 = torch.empty((M, D), device=dev, dtype=torch.float32)
+            ops.gemm(a, self._w(mlp.fc2.weight, lp), mlp.fc2.bias.detach(), x2, x1, _K, _K, _E["residual"], 1, 0)
+            if save:
+                st.blocks.append((x, h, mean1, rstd1, qkv, o, aux, x1, h2, mean2, rstd2, u, a))
+            x = x2
+
+        cls_rows = x.view(B, N, D)[:, 0].contiguous()
+        nf = self.norm
+        feats, meanf, rstdf = ops.layernorm_fwd(cls_rows, nf.weight.detach(), nf.bias.detach(), nf.eps, False)
+        if save:
+            st.cls_rows, st.meanf, st.rstdf = cls_rows, meanf, rstdf
+        return feats, st
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def _linear_bwd(self, dy: Tensor, x_in: Tensor, lin: nn.Linear, lp: bool, need_dx: bool,
+                    dgelu_aux: Optional[Tensor] = None) -> Optional[Tensor]:
+        """Gradients of y = x W^T + b given dy [M, out]: accumulates dW, db; returns dx (or None)."""
+        M = dy.shape[0]
+        out_f, in_f = lin.weight.shape
+        if lin.weight.requires_grad:
+            ops.gemm(dy, x_in, None, _grad_buffer(lin.weight), None, _MN, _MN, _E["accum"],
+                     _split_k_for(out_f, in_f, M) if lp else 1, 0)
+        if lin.bias is not None and lin.bias.requires_grad:
+            ops.colsum(dy, _grad_buffer(lin.bias), True)
+        if not need_dx:
+            return None
+        dx = torch.empty((M, in_f), device=dy.device, dtype=dy.dtype)
+        if dgelu_aux is not None:
+            ops.gemm(dy, self._w(lin.weight, lp), None, dx, dgelu_aux, _K, _MN, _E["dgelu"], 1, 0)
+        else:
+            ops.gemm(dy, self._w(lin.weight, lp), None, dx, None, _K, _MN, _E["none"], 1, 0)
+        return dx
+
+    def _ln_bwd(self, dy: Tensor, x: Tensor, ln: nn.LayerNorm, mean: Tensor, rstd: Tensor,
+                dres: Optional[Tensor], lp: bool) -> Tuple[Tensor, Tensor]:
+        if ln.weight.requires_grad:
+            dg, db = _grad_buffer(ln.weight), _grad_buffer(ln.bias)
+        else:
+            dg = torch.zeros_like(ln.weight)
+            db = torch.zeros_like(ln.bias)
+        dx, dx_lp = ops.layernorm_bwd(dy, x, ln.weight.detach(), mean, rstd, dres, dg, db, lp)
+        return dx, (dx_lp if lp else dx)
+
+    def _backward_impl(self, st: _Saved, dfeats: Tensor) -> None:
+        lp, B, N = st.lp, st.B, st.N
+        D = self.embed_dim
+        M = B * N
+        dev = dfeats.device
+        dcls, _ = self._ln_bwd(dfeats.float().contiguous(), st.cls_rows, self.norm, st.meanf, st.rstdf, None, False)
+        dx = torch.zeros((M, D), device=dev, dtype=torch.float32)
+        dx.view(B, N, D)[:, 0] = dcls
+        dy = _to_bf16(dx) if lp else dx
+
+        for blk, saved in zip(reversed(self.blocks), reversed(st.blocks)):
+            (x, h, mean1, rstd1, qkv, o, aux, x1, h2, mean2, rstd2, u, a) = saved
+            # MLP branch: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
+            du = self._linear_bwd(dy, a, blk.mlp.fc2, lp, True, dgelu_aux=u)
+            dh2 = self._linear_bwd(du, h2, blk.mlp.fc1, lp, True)
+            dx1, dy1 = self._ln_bwd(dh2, x1, blk.norm2, mean2, rstd2, dx, lp)
+            # attention branch: x1 = x + proj(attn(qkv(LN1(x))))
+            do = self._linear_bwd(dy1, o, blk.attn.proj, lp, True)
+            dqkv = self._attention_bwd(qkv, o, do, aux, B, N, lp)
+            dh = self._linear_bwd(dqkv, h, blk.attn.qkv, lp, True)
+            dx, dy = self._ln_bwd(dh, x, blk.norm1, mean1, rstd1, dx1, lp)
+
+        # embedding: x0[b] = cat(cls, patches[b] W^T + b) + pos
+        if self.pos_embed.requires_grad:
+            ops.colsum(dx.view(B, N * D), _grad_buffer(self.pos_embed).view(N * D), True)
+        if self.cls_token.requires_grad:
+            ops.colsum(dx.view(B, N * D)[:, :D], _grad_buffer(self.cls_token).view(D), True)
+        proj = self.patch_embed.proj
+        if proj.weight.requires_grad or proj.bias.requires_grad:
+            dpatch = dy.view(B, N, D)[:, 1:].reshape(B * (N - 1), D)
+            if proj.weight.requires_grad:
+                gw = _grad_buffer(proj.weight)
+                ops.gemm(dpatch, st.patches, None, gw.view(D, -1), None, _MN, _MN, _E["accum"],
+                         _split_k_for(D, gw.numel() // D, B * (N - 1)) if lp else 1, 0)
+            if proj.bias.requires_grad:
+                ops.colsum(dpatch, _grad_buffer(proj.bias), True)
+
+
+class _VitFunction(torch.autograd.Function):
+    """Whole-backbone autograd node. Parameter gradients are accumulated by the kernels straight
+    into ``p.grad`` (the FlatArena gradient buffer when there is one), so ``backward`` returns
+    ``None`` for them: no per-tensor AccumulateGrad copies, and gradient accumulation across
+    micro-steps (reference train.py:151-155) is the kernels' own ``+=``."""
+
+    @staticmethod
+    def forward(ctx, vit: VisionTransformer, img: Tensor, lp: bool, *params):
+        feats, st = vit._forward_impl(img, lp, save=True)
+        ctx.vit = vit
+        ctx.st = st
+        ctx.nparams = len(params)
+        return feats
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dfeats: Tensor):
+        st, ctx.st = ctx.st, None
+        if st is None:
+            raise RuntimeError("fedvit backbone: backward called twice on the same graph")
+        ctx.vit._backward_impl(st, dfeats)
+        return (None, None, None) + (None,) * ctx.nparams
+
+
+def create_model(model_name: str, pretrained: bool = False, num_classes: int = 0,
+                 drop_path_rate: float = 0.0, in_chans: int = 3, **kwargs) -> VisionTransformer:
+    """Signature of ``timm.create_model`` as the reference calls it (model.py:112-117)."""
+    if kwargs:
+        raise TypeError(f"unsupported create_model arguments: {sorted(kwargs)}")
+    if pretrained:
+        raise RuntimeError(
+            "pretrained=True needs timm's weight download, which this environment cannot do; "
+            "set model.pretrained: false and load a timm ViT state_dict instead (keys are identical)"
+        )
+    d, l, h, patch, img = parse_vit_name(model_name)
+    return VisionTransformer(img_size=img, patch_size=patch, in_chans=in_chans, num_classes=num_classes,
+                             embed_dim=d, depth=l, num_heads=h, drop_path_rate=drop_path_rate)

@@ -1,0 +1,282 @@
+"""Kernel parity on a real B200: every libfedvit entry point, through the C ABI, against a plain
+PyTorch fp32 reference of the same op (tolerances: 1e-4 relative for fp32 arithmetic, 2e-2 for
+bf16 — the north_star gates — tighter where the op is exact)."""
+import math
+
+import pytest
+import torch
+
+import fedvit_b200  # noqa: F401
+from conftest import rel_err
+from fedvit_b200 import ops
+from fedvit_b200._lib import FedVitError, launch_count
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _gen(seed):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+def _gemm_ref(a, b, am, bm):
+    A = a.double() if am == 0 else a.double().t()
+    B = b.double() if bm == 0 else b.double().t()
+    return (A @ B.t()).float()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1000, 776, 328), (3152, 576, 192), (5, 8, 8), (4097, 2304, 768)])
+@pytest.mark.parametrize("am,bm", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_gemm_bf16_all_layouts(m, n, k, am, bm):
+    if am == 1 and m % 8:
+        m = (m + 7) // 8 * 8  # MN-major A needs a 16-byte aligned leading dimension
+    g = _gen(m + n + k)
+    a = torch.randn((m, k) if am == 0 else (k, m), device=DEV, generator=g).bfloat16()
+    b = torch.randn((n, k) if bm == 0 else (k, n), device=DEV, generator=g).bfloat16()
+    bias = torch.randn(n, device=DEV, generator=g)
+    out = torch.empty(m, n, device=DEV)
+    ops.gemm(a, b, bias, out, None, am, bm, ops.EPI["none"], 1, 0)
+    assert rel_err(out, _gemm_ref(a, b, am, bm) + bias) < 1e-5  # bf16 inputs are exact in fp32; fp32 accumulate
+
+
+def test_gemm_bf16_epilogues():
+    m, n, k = 777, 520, 200
+    g = _gen(1)
+    a = torch.randn(m, k, device=DEV, generator=g).bfloat16()
+    b = torch.randn(n, k, device=DEV, generator=g).bfloat16()
+    bias = torch.randn(n, device=DEV, generator=g)
+    ref = _gemm_ref(a, b, 0, 0)
+    # bf16 store
+    out = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, b, bias, out, None, 0, 0, ops.EPI["none"], 1, 0)
+    assert rel_err(out, ref + bias) < 4e-3
+    # + residual (fp32)
+    res = torch.randn(m, n, device=DEV, generator=g)
+    out = torch.empty(m, n, device=DEV)
+    ops.gemm(a, b, bias, out, res, 0, 0, ops.EPI["residual"], 1, 0)
+    assert rel_err(out, ref + bias + res) < 1e-5
+    # GELU with saved pre-activation, fp32 and bf16 stores
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 4e-3)):
+        o, pre = torch.empty(m, n, device=DEV, dtype=dt), torch.empty(m, n, device=DEV, dtype=dt)
+        ops.gemm_gelu(a, b, bias, o, pre)
+        assert rel_err(pre, ref + bias) < tol
+        assert rel_err(o, torch.nn.functional.gelu(pre.float())) < tol
+    # dgrad fused with GELU'
+    u = torch.randn(m, n, device=DEV, generator=g)
+    ur = u.clone().requires_grad_(True)
+    torch.nn.functional.gelu(ur).sum().backward()
+    out = torch.empty(m, n, device=DEV)
+    ops.gemm(a, b, None, out, u, 0, 0, ops.EPI["dgelu"], 1, 0)
+    assert rel_err(out, ref * ur.grad) < 1e-5
+    # accumulate + split-K
+    for sk in (1, 3):
+        acc = torch.randn(m, n, device=DEV, generator=g)
+        want = acc + ref
+        ops.gemm(a, b, None, acc, None, 0, 0, ops.EPI["accum"], sk, 0)
+        assert rel_err(acc, want) < 1e-5
+    # patch epilogue: rows scattered past one cls slot per image, + pos_embed
+    tokens, imgs = 37, 21
+    a = torch.randn(tokens * imgs, k, device=DEV, generator=g).bfloat16()
+    pos = torch.randn(tokens + 1, n, device=DEV, generator=g)
+    x = torch.zeros(imgs * (tokens + 1), n, device=DEV)
+    ops.gemm(a, b, bias, x, pos, 0, 0, ops.EPI["patch"], 1, tokens)
+    want = (_gemm_ref(a, b, 0, 0) + bias).view(imgs, tokens, n) + pos[1:]
+    assert rel_err(x.view(imgs, tokens + 1, n)[:, 1:], want) < 1e-5
+    assert float(x.view(imgs, tokens + 1, n)[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("am,bm", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_gemm_f32_layouts(am, bm):
+    m, n, k = 197, 130, 77
+    g = _gen(5)
+    a = torch.randn((m, k) if am == 0 else (k, m), device=DEV, generator=g)
+    b = torch.randn((n, k) if bm == 0 else (k, n), device=DEV, generator=g)
+    bias = torch.randn(n, device=DEV, generator=g)
+    out = torch.empty(m, n, device=DEV)
+    ops.gemm(a, b, bias, out, None, am, bm, 0, 1, 0)
+    assert rel_err(out, _gemm_ref(a, b, am, bm) + bias) < 1e-6
+
+
+def test_gemm_rejects_bad_arguments():
+    a = torch.zeros(16, 16, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(FedVitError):
+        ops.gemm(a, a, None, torch.zeros(16, 12, device=DEV), None, 0, 0, 0, 1, 0)  # shape mismatch
+    with pytest.raises(FedVitError):
+        ops.gemm(a, a, torch.zeros(16, device=DEV, dtype=torch.bfloat16), torch.zeros(16, 16, device=DEV), None, 0, 0, 0, 1, 0)
+    with pytest.raises(FedVitError):  # C ABI argument check: ldc must keep 16-byte rows
+        ops.gemm(a, a, None, torch.zeros(16, 20, device=DEV)[:, :16], None, 0, 0, 0, 1, 0)
+    with pytest.raises(FedVitError):
+        ops.gemm(a, a, None, torch.zeros(16, 16, device=DEV), None, 0, 0, ops.EPI["residual"], 1, 0)  # aux missing
+    with pytest.raises(FedVitError):
+        ops.gemm(a.cpu(), a.cpu(), None, torch.zeros(16, 16), None, 0, 0, 0, 1, 0)  # no CPU fallback
+
+
+@pytest.mark.parametrize("cols", [64, 192, 768, 1024])
+def test_layernorm_fwd_bwd(cols):
+    rows = 1031
+    g = _gen(cols)
+    x = torch.randn(rows, cols, device=DEV, generator=g) * 2 + 0.5
+    gam, bet = torch.randn(cols, device=DEV, generator=g), torch.randn(cols, device=DEV, generator=g)
+    dy, dres = torch.randn(rows, cols, device=DEV, generator=g), torch.randn(rows, cols, device=DEV, generator=g)
+    xr, gr, br = x.double().requires_grad_(True), gam.double().requires_grad_(True), bet.double().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (cols,), gr, br, 1e-6)
+    yr.backward(dy.double())
+    y, mean, rstd = ops.layernorm_fwd(x, gam, bet, 1e-6, False)
+    assert rel_err(y, yr) < 1e-6
+    assert rel_err(mean, x.double().mean(1)) < 1e-6
+    dg, db = torch.zeros(cols, device=DEV), torch.zeros(cols, device=DEV)
+    dx, dxlp = ops.layernorm_bwd(dy, x, gam, mean, rstd, dres, dg, db, True)
+    assert rel_err(dx, xr.grad + dres.double()) < 1e-5
+    assert rel_err(dxlp, dx.bfloat16()) == 0.0
+    assert rel_err(dg, gr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
+    ops.layernorm_bwd(dy, x, gam, mean, rstd, None, dg, db, False)  # accumulates
+    assert rel_err(dg, 2 * gr.grad) < 1e-5
+    ybf, _, _ = ops.layernorm_fwd(x, gam, bet, 1e-6, True)
+    assert rel_err(ybf, yr) < 4e-3
+    dxb, _ = ops.layernorm_bwd(dy.bfloat16(), x, gam, mean, rstd, None, torch.zeros_like(dg), torch.zeros_like(db), False)
+    assert rel_err(dxb, xr.grad) < 1e-2
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (1, 577, 2), (3, 64, 1), (2, 65, 2), (1, 1, 1)])
+def test_flash_attention_fwd_bwd(B, N, H):
+    g = _gen(N)
+    qkv = torch.randn(B * N, 3 * H * 64, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B * N, H * 64, device=DEV, generator=g).bfloat16()
+    scale = 1.0 / math.sqrt(64)
+    q, k, v = (qkv.double().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)[i].clone().requires_grad_(True) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * scale
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, H * 64)
+    o.backward(dout.double())
+    out, lse = ops.attention_fwd(qkv, B, N, H, scale)
+    assert rel_err(out, o) < 2e-2 and rel_err(out, o) < 5e-3
+    assert rel_err(lse, torch.logsumexp(s, -1)) < 1e-5
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).float().view(B * N, 3, H * 64)
+    ref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B * N, 3, H * 64)
+    for i, name in enumerate("qkv"):
+        assert rel_err(dqkv[:, i], ref[:, i]) < 1e-2, name
+    # bit-reproducible (no atomics on the attention path)
+    assert torch.equal(ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).view(B * N, 3, H * 64).float(), dqkv)
+
+
+def _asl_ref(logits, targets, gn=4.0, gp=1.0, clip=0.05, eps=1e-8):
+    from oracle import asl
+    return asl.asymmetric_focal_loss(logits, targets, gn, gp, clip, eps)
+
+
+@pytest.mark.parametrize("B,C", [(4, 7), (256, 7), (33, 8), (1, 3), (1024, 7)])
+def test_fused_losses_match_oracle(B, C):
+    g = _gen(B)
+    logits = (torch.randn(B, C, device=DEV, generator=g) * 3)
+    targets = torch.randint(0, C, (B,), device=DEV, generator=g)
+    lc = logits.cpu().requires_grad_(True)
+    ref = _asl_ref(lc, targets.cpu())
+    ref.backward()
+    loss, dl = ops.asl_loss(logits, targets, 4.0, 1.0, 0.05, 1e-8)
+    assert float(loss) == pytest.approx(float(ref), rel=1e-5)
+    assert rel_err(dl, lc.grad) < 1e-5
+    lc.grad = None
+    ce = torch.nn.functional.cross_entropy(lc, targets.cpu())
+    ce.backward()
+    loss, dl = ops.ce_loss(logits, targets)
+    assert float(loss) == pytest.approx(float(ce), rel=1e-5)
+    assert rel_err(dl, lc.grad) < 1e-5
+
+
+def test_loss_known_answers_on_gpu(asl_kats):
+    k = asl_kats
+    for i in (1, 2, 3):
+        lg = torch.from_numpy(k[f"kat{i}_logits"]).to(DEV)
+        t = torch.from_numpy(k[f"kat{i}_targets"]).to(DEV)
+        loss, dl = ops.asl_loss(lg, t, 4.0, 1.0, 0.05, 1e-8)
+        assert float(loss) == pytest.approx(float(k[f"kat{i}_loss"]), rel=2e-6)
+        if f"kat{i}_dlogits" in k:
+            assert torch.allclose(dl.cpu(), torch.from_numpy(k[f"kat{i}_dlogits"]), rtol=1e-4, atol=1e-7)
+
+
+def test_adamw_sweep_matches_torch_adamw():
+    n = 1 << 18
+    g = _gen(1)
+    p0 = torch.randn(n, device=DEV, generator=g)
+    cuts = [n // 4, n // 2, n]
+    lrs, wds = [1e-3, -1.0, 3e-3], [1e-2, 0.0, 1e-5]
+    ps = [p0[: cuts[0]].clone().requires_grad_(True), p0[cuts[0]: cuts[1]].clone().requires_grad_(True),
+          p0[cuts[1]:].clone().requires_grad_(True)]
+    opt = torch.optim.AdamW([{"params": [ps[0]], "lr": lrs[0], "weight_decay": wds[0]},
+                             {"params": [ps[2]], "lr": lrs[2], "weight_decay": wds[2]}])
+    pp, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ema, ema_ref = p0.clone(), p0.clone()
+    plp = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    seg = (torch.tensor(cuts, device=DEV), torch.tensor(lrs, device=DEV), torch.tensor(wds, device=DEV))
+    ss = torch.zeros(1, device=DEV)
+    for step in (1, 2, 3):
+        grad = torch.randn(n, device=DEV, generator=g) * (0.02 if step < 3 else 1e-5)
+        for q, sl in zip(ps, (slice(0, cuts[0]), slice(cuts[0], cuts[1]), slice(cuts[1], n))):
+            q.grad = grad[sl].clone()
+        total = torch.nn.utils.clip_grad_norm_(ps, 1.0)  # the norm covers the never-stepped range too
+        opt.step()
+        ops.sumsq(grad, ss, False)
+        assert float(ss.sqrt()) == pytest.approx(float(total), rel=1e-5)
+        ops.adamw_flat(pp, grad, m, v, *seg, ss, 1.0, 0.9, 0.999, 1e-8, step, ema, 0.99, plp)
+        now = torch.cat([q.detach() for q in ps])
+        ema_ref.mul_(0.99).add_(now, alpha=0.01)
+    ref = torch.cat([q.detach() for q in ps])
+    assert rel_err(pp, ref) < 1e-6
+    assert torch.equal(pp[cuts[0]: cuts[1]], p0[cuts[0]: cuts[1]])  # lr < 0: untouched
+    assert rel_err(ema, ema_ref) < 1e-6
+    assert torch.equal(plp, pp.bfloat16())
+    g2 = grad.clone()
+    ops.scale_by_clip(g2, torch.full((1,), 100.0, device=DEV), 1.0)
+    assert rel_err(g2, grad * (1.0 / (10.0 + 1e-6))) < 1e-6
+
+
+def test_fedavg_fold_is_bit_exact_against_oracle():
+    from oracle import fedavg as ofed
+    n = (1 << 20) + 64
+    g = _gen(2)
+    ws = [torch.randn(n, device=DEV, generator=g) for _ in range(5)]
+    n_k = [100, 250, 50, 300, 300]
+    acc = torch.empty(n, device=DEV)
+    for i, (w, c) in enumerate(zip(ws, ofed.client_weights(n_k))):
+        ops.fedavg_accum(acc, w, c, i == 0)
+    want = ofed.fedavg_flat([w.cpu() for w in ws], n_k)
+    assert torch.equal(acc.cpu(), want)
+    # properties at full ViT-B arena size: identical clients average to themselves; linear in w
+    n = 86_196_224
+    w = torch.randn(n, device=DEV, generator=g)
+    acc = torch.empty(n, device=DEV)
+    for i, c in enumerate(ofed.client_weights([4096] * 8)):
+        ops.fedavg_accum(acc, w, c, i == 0)
+    assert rel_err(acc, w) < 1e-6
+    acc2 = torch.empty(n, device=DEV)
+    ops.fedavg_accum(acc2, w * 2, 0.5, True)
+    assert torch.equal(acc2, w)
+
+
+def test_elementwise_helpers():
+    g = _gen(3)
+    img = torch.randn(3, 4, 224, 224, device=DEV, generator=g)
+    ref = torch.nn.functional.unfold(img, 16, stride=16).transpose(1, 2).reshape(-1, 4 * 256)
+    assert torch.equal(ops.patchify(img, False), ref)
+    assert torch.equal(ops.patchify(img, True), ref.bfloat16())
+    a = torch.randn(5000, 770, device=DEV, generator=g)
+    out = torch.zeros(770, device=DEV)
+    ops.colsum(a, out, False)
+    assert rel_err(out, a.double().sum(0)) < 1e-5
+    ops.colsum(a.bfloat16(), out, True)
+    assert rel_err(out, a.double().sum(0) + a.bfloat16().double().sum(0)) < 1e-5
+    s = torch.randn(37, 197, device=DEV, generator=g)
+    p = ops.softmax_rows(s, 0.125)
+    assert rel_err(p, (s.double() * 0.125).softmax(-1)) < 1e-6
+    dp = torch.randn_like(s)
+    sr = s.double().requires_grad_(True)
+    ((sr * 0.125).softmax(-1) * dp.double()).sum().backward()
+    assert rel_err(ops.softmax_rows_bwd(p, dp, 0.125), sr.grad) < 1e-5
+    n0 = launch_count()
+    ops.cast_bf16(a.view(-1)[: 4096], torch.empty(4096, device=DEV, dtype=torch.bfloat16))
+    assert launch_count() == n0 + 1

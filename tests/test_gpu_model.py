@@ -1,0 +1,296 @@
+"""End-to-end parity on a real B200, through the reference-facing API (build_model / forward /
+build_loss / train_one_epoch / FedAvg round), against (a) the fixtures written by the reference's
+own code and (b) the CPU oracle on seeded inputs. Gates (north_star): logits and gradients within
+1e-4 relative in fp32 and 2e-2 in bf16; FedAvg aggregate within 1e-6 (bit-exact on one GPU);
+identical label predictions on a fixed eval batch."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import fedvit_b200  # noqa: F401
+from conftest import micro_config, rel_err, state_from_golden
+from fedvit_b200 import data, fedavg, losses, model, optim, train, utils
+from fedvit_b200.arena import FlatArena
+from oracle import asl, fedavg as ofed, isic, step
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda")
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _grad_errs(ours: torch.nn.Module, want: dict):
+    """max over parameters of ||g - g_ref|| / max(||g_ref||, 1e-3 * global norm)."""
+    total = float(np.sqrt(sum(float(np.sum(np.square(v.astype(np.float64)))) for v in want.values())))
+    worst, who = 0.0, None
+    for n, p in ours.named_parameters():
+        ref = torch.from_numpy(np.asarray(want[n])).double()
+        err = float((p.grad.detach().double().cpu() - ref).norm() / max(float(ref.norm()), 1e-3 * total))
+        if err > worst:
+            worst, who = err, n
+    return worst, who
+
+
+def _fixture_model(g, masked=False):
+    m = model.build_model(micro_config(masked)).to(DEV)
+    m.load_state_dict(state_from_golden(g))
+    return m.train()
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_fp32_forward_backward_matches_reference_fixture(golden_rgb, golden_masked, masked):
+    g = golden_masked if masked else golden_rgb
+    m = _fixture_model(g, masked)
+    x, y = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["y"]).to(DEV)
+    logits = m(x)["logits"]
+    logits.retain_grad()
+    loss = losses.build_loss(micro_config())(logits, y)
+    loss.backward()
+    assert rel_err(logits, torch.from_numpy(g["logits"])) < 1e-4
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-4)
+    assert rel_err(logits.grad, torch.from_numpy(g["dlogits"])) < 1e-4
+    worst, who = _grad_errs(m, {k[5:]: v for k, v in g.items() if k.startswith("grad/")})
+    assert worst < 1e-4, (who, worst)
+    assert torch.equal(logits.argmax(1).cpu(), torch.from_numpy(g["logits"]).argmax(1))
+
+
+def test_two_fused_steps_match_reference_fixture(golden_rgb):
+    """clip(1.0) + AdamW over the reference's LLRD groups + EMA, two steps — the fixture was written
+    by torch.optim.AdamW / utils.clip_grad_norm / utils.EMA of the reference (make_golden.py)."""
+    g = golden_rgb
+    m = _fixture_model(g)
+    arena = FlatArena(m)
+    opt = optim.FusedAdamW(model.get_layerwise_lr_groups(m, 1e-3, 0.75, 1e-2), weight_decay=1e-2, arena=arena)
+    ema = utils.EMA(m, decay=0.9).attach(opt)
+    crit = losses.build_loss(micro_config())
+    x, y = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["y"]).to(DEV)
+    for i in range(2):
+        opt.zero_grad(set_to_none=True)
+        crit(m(x)["logits"], y).backward()
+        norm = utils.clip_grad_norm(m.parameters(), 1.0, optimizer=opt)
+        if i == 0:
+            assert float(norm) == pytest.approx(float(g["grad_norm"]), rel=1e-4)
+        opt.step()
+        ema.update()
+    for n, p in m.named_parameters():
+        assert rel_err(p, torch.from_numpy(g[f"after2/{n}"])) < 1e-5, n
+        assert rel_err(ema.shadow[n], torch.from_numpy(g[f"ema2/{n}"])) < 1e-5, n
+    assert torch.equal(m.backbone.cls_token.cpu(), torch.from_numpy(g["state/backbone.cls_token"]))  # never stepped
+    m.eval()
+    with torch.no_grad():
+        ev = m(x)["logits"]
+    assert rel_err(ev, torch.from_numpy(g["eval_logits_after2"])) < 1e-4
+    assert torch.equal(ev.argmax(1).cpu(), torch.from_numpy(g["eval_logits_after2"]).argmax(1))
+    # EMA swap-in / restore round trip (reference train.py:289-295)
+    before = arena.params.clone()
+    ema.apply_shadow()
+    assert rel_err(m.backbone.norm.weight, torch.from_numpy(g["ema2/backbone.norm.weight"])) < 1e-5
+    ema.restore()
+    assert torch.equal(arena.params, before)
+
+
+def _tiny_pair(seed=0, masked=False, batch=8):
+    cfg = {"model": {"backbone": "vit_tiny_patch16_224", "num_classes": 7, "image_size": 224, "pretrained": False,
+                     "drop_path_rate": 0.0, "metadata": {"enabled": False}, "classifier": {"hidden_dim": 512, "dropout": 0.0}},
+           "data": {"use_segmentation_mask": masked}}
+    torch.manual_seed(seed)
+    ora = isic.model_from_config(cfg).train()
+    with torch.no_grad():
+        for p in ora.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.05)
+    ours = model.build_model(cfg)
+    ours.load_state_dict(ora.state_dict())
+    ours = ours.to(DEV).train()
+    g = torch.Generator().manual_seed(1000)
+    x = torch.randn(batch, 4 if masked else 3, 224, 224, generator=g)
+    y = torch.randint(0, 7, (batch,), generator=g)
+    return cfg, ora, ours, x, y
+
+
+def _oracle_grads(ora, x, y):
+    ora.zero_grad(set_to_none=True)
+    logits = ora(x)["logits"]
+    loss = asl.asymmetric_focal_loss(logits, y)
+    loss.backward()
+    return logits.detach(), float(loss), {n: p.grad.numpy() for n, p in ora.named_parameters()}
+
+
+def test_vit_tiny_fp32_vs_oracle():
+    """BASELINE config 1 shapes (ViT-Tiny/16 224, 7 classes), fp32 arithmetic."""
+    _, ora, ours, x, y = _tiny_pair()
+    want_logits, want_loss, want_grads = _oracle_grads(ora, x, y)
+    logits = ours(x.to(DEV))["logits"]
+    loss = losses.AsymmetricFocalLoss()(logits, y.to(DEV))
+    loss.backward()
+    assert rel_err(logits, want_logits) < 1e-4
+    assert float(loss) == pytest.approx(want_loss, rel=1e-4)
+    worst, who = _grad_errs(ours, want_grads)
+    assert worst < 1e-4, (who, worst)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_vit_tiny_bf16_vs_oracle(masked):
+    """bf16 tensor-core path under autocast vs the fp32 oracle: 2e-2 gate, identical predictions."""
+    _, ora, ours, x, y = _tiny_pair(seed=1, masked=masked)
+    want_logits, want_loss, want_grads = _oracle_grads(ora, x, y)
+    FlatArena(ours)
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        logits = ours(x.to(DEV))["logits"]
+        loss = losses.AsymmetricFocalLoss()(logits, y.to(DEV))
+    loss.backward()
+    assert rel_err(logits, want_logits) < 2e-2
+    assert float(loss) == pytest.approx(want_loss, rel=2e-2)
+    worst, who = _grad_errs(ours, want_grads)
+    assert worst < 2e-2, (who, worst)
+    ours.eval(), ora.eval()
+    with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        pred = ours(x.to(DEV))["logits"].argmax(1).cpu()
+    with torch.no_grad():
+        assert torch.equal(pred, ora(x)["logits"].argmax(1))
+
+
+def test_gradient_accumulation_and_frozen_backbone():
+    _, ora, ours, x, y = _tiny_pair(seed=2, batch=4)
+    crit = losses.AsymmetricFocalLoss()
+    xd, yd = x.to(DEV), y.to(DEV)
+    crit(ours(xd)["logits"], yd).backward()
+    once = {n: p.grad.clone() for n, p in ours.named_parameters()}
+    crit(ours(xd)["logits"], yd).backward()  # second micro-batch accumulates (train.py:151-155)
+    for n, p in ours.named_parameters():
+        assert rel_err(p.grad, 2 * once[n]) < 1e-5, n
+    ours.zero_grad(set_to_none=True)
+    ours.freeze_backbone()
+    crit(ours(xd)["logits"], yd).backward()
+    assert all(p.grad is None for p in ours.backbone.parameters())
+    assert all(p.grad is not None for p in ours.classifier.parameters())
+
+
+def test_train_one_epoch_matches_oracle_local_epoch(golden_rgb):
+    cfg = micro_config()
+    m = _fixture_model(golden_rgb)
+    ora = isic.model_from_config(cfg)
+    ora.load_state_dict(state_from_golden(golden_rgb))
+    loader = data.SyntheticClientLoader(0, 24, 6, 32, channels=3, num_classes=7, pin=False)
+    batches = [{k: v.clone() for k, v in b.items()} for b in loader]
+    arena = FlatArena(m)
+    opt = optim.FusedAdamW(model.get_layerwise_lr_groups(m, 1e-3, 0.75, 1e-2), weight_decay=1e-2, arena=arena)
+    ema = utils.EMA(m, decay=0.9).attach(opt)
+    got = train.train_one_epoch(m, loader, losses.build_loss(cfg), opt, None, None, ema, DEV, cfg, 1, None)
+    oopt = torch.optim.AdamW(isic.llrd_groups(ora, 1e-3, 0.75, 1e-2), weight_decay=1e-2)
+    oema = step.OracleEMA(ora, 0.9)
+    want = step.local_epoch(ora, batches, asl.loss_from_config(cfg), oopt, grad_clip=1.0, ema=oema)
+    assert got == pytest.approx(want, rel=1e-4)
+    for n, p in ora.named_parameters():
+        assert rel_err(dict(m.named_parameters())[n], p) < 1e-4, n
+        assert rel_err(ema.shadow[n], oema.shadow[n]) < 1e-4, n
+    # gradient accumulation path: 2 micro-batches per step
+    cfg2 = micro_config()
+    cfg2["training"]["gradient_accumulation_steps"] = 2
+    m2 = _fixture_model(golden_rgb)
+    ora2 = isic.model_from_config(cfg)
+    ora2.load_state_dict(state_from_golden(golden_rgb))
+    opt2 = optim.FusedAdamW(model.get_layerwise_lr_groups(m2, 1e-3, 0.75, 1e-2), weight_decay=1e-2, arena=FlatArena(m2))
+    got2 = train.train_one_epoch(m2, loader, losses.build_loss(cfg), opt2, None, None, None, DEV, cfg2, 1, None)
+    want2 = step.local_epoch(ora2, batches, asl.loss_from_config(cfg), torch.optim.AdamW(isic.llrd_groups(ora2, 1e-3, 0.75, 1e-2), weight_decay=1e-2),
+                             grad_clip=1.0, accum_steps=2)
+    assert got2 == pytest.approx(want2, rel=1e-4)
+    assert rel_err(m2.classifier[0].weight, ora2.classifier[0].weight) < 1e-4
+
+
+def test_validate_reports_reference_metrics(golden_rgb):
+    cfg = micro_config()
+    m = _fixture_model(golden_rgb)
+    loader = data.SyntheticClientLoader(5, 30, 6, 32, num_classes=7, pin=False)
+    out = train.validate(m, loader, losses.build_loss(cfg), DEV, cfg)
+    ora = isic.model_from_config(cfg).eval()
+    ora.load_state_dict(state_from_golden(golden_rgb))
+    ys, ps, ls = [], [], []
+    with torch.no_grad():
+        for b in loader:
+            lg = ora(b["image"])["logits"]
+            ls.append(float(asl.asymmetric_focal_loss(lg, b["label"])) * 6)
+            ps.append(lg.argmax(1)), ys.append(b["label"])
+    want = train.classification_metrics(torch.cat(ys).numpy(), torch.cat(ps).numpy(), 7)
+    assert out["loss"] == pytest.approx(sum(ls) / 30, rel=1e-4)
+    for k in ("accuracy", "balanced_accuracy", "macro_f1"):
+        assert out[k] == pytest.approx(want[k])
+
+
+def test_fedavg_round_single_gpu_matches_oracle(golden_rgb):
+    """Config-1 shape of a round (2 clients, 1 local epoch) on the toy model: the whole round loop
+    (restart from global, local epoch, weighted fold, install) vs the oracle doing the same on CPU;
+    the aggregate step itself is bit-exact."""
+    cfg = micro_config()
+    cfg["federated"] = {"num_clients": 2, "rounds": 1, "local_epochs": 1, "samples_per_client": [24, 12]}
+    cfg["training"]["optimizer"] = {"lr": 1e-3, "weight_decay": 1e-2}
+    torch.manual_seed(42)
+    out = train.run_federated(cfg, device=DEV)
+    ours = out["model"]
+    # oracle: same initial weights (seeded build), same shards
+    utils.seed_everything(42)
+    init = model.build_model(cfg).state_dict()
+    finals, sizes = [], [24, 12]
+    for c in range(2):
+        ora = isic.model_from_config(cfg)
+        ora.load_state_dict(init)
+        loader = data.SyntheticClientLoader(c, sizes[c], 6, 32, num_classes=7, pin=False)
+        oopt = torch.optim.AdamW(isic.llrd_groups(ora, 1e-3, 0.75, 1e-2), weight_decay=1e-2)
+        step.local_epoch(ora, list(loader), asl.loss_from_config(cfg), oopt, grad_clip=1.0)
+        finals.append({k: v.clone() for k, v in ora.state_dict().items()})
+    want = ofed.fedavg_state_dicts(finals, sizes)
+    for k, v in ours.state_dict().items():
+        assert rel_err(v, want[k]) < 1e-4, k
+    assert out["rounds"][0]["images_per_s"] > 0
+    # the aggregate alone: arena fold vs oracle on identical client weights -> bit exact
+    arena = out["arena"]
+    agg = fedavg.FedAvgAggregator(ours, arena)
+    agg.begin_round()
+    flats = []
+    for c in range(3):
+        agg.load_global()
+        arena.params.add_(torch.randn(arena.numel, device=DEV, generator=torch.Generator(device="cuda").manual_seed(c)) * 0.01)
+        flats.append(arena.params.detach().cpu().clone())
+        agg.fold([5, 9, 2][c], 16, client_id=c)
+    agg.finish()
+    assert torch.equal(arena.params.cpu(), ofed.fedavg_flat(flats, [5, 9, 2]))
+    got = fedavg.fedavg_state_dicts(finals, sizes, device=DEV)
+    for k in want:
+        assert torch.equal(got[k].cpu(), want[k]), k
+
+
+def test_vit_base_full_size_properties():
+    """BASELINE config 2 at full size (ViT-B/16, batch 256, bf16): finite logits / loss / grads,
+    eval forward deterministic, a full fused step moves the weights, bf16 shadow tracks them."""
+    cfg = {"model": {"backbone": "vit_base_patch16_224", "num_classes": 7, "image_size": 224, "pretrained": False,
+                     "drop_path_rate": 0.0, "metadata": {"enabled": False}, "classifier": {"hidden_dim": 512, "dropout": 0.0}}}
+    torch.manual_seed(0)
+    m = model.build_model(cfg).to(DEV).train()
+    assert model.count_parameters(m) == 86_195_975
+    arena = FlatArena(m)
+    opt = optim.FusedAdamW(model.get_layerwise_lr_groups(m), weight_decay=1e-5, arena=arena)
+    x = torch.randn(256, 3, 224, 224, device=DEV)
+    y = torch.randint(0, 7, (256,), device=DEV)
+    before = arena.params.clone()
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        logits = m(x)["logits"]
+        loss = losses.AsymmetricFocalLoss()(logits, y)
+    loss.backward()
+    assert torch.isfinite(logits).all() and torch.isfinite(loss)
+    assert torch.isfinite(arena.grads).all() and float(arena.grads.abs().sum()) > 0
+    norm = utils.clip_grad_norm(m.parameters(), 1.0, optimizer=opt)
+    opt.step()
+    assert torch.isfinite(norm) and torch.isfinite(arena.params).all()
+    assert not torch.equal(arena.params, before)
+    assert torch.equal(arena.lp, arena.params.bfloat16())
+    assert torch.equal(m.backbone.pos_embed, arena.view(before, "backbone.pos_embed"))  # never stepped
+    m.eval()
+    with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        a, b = m(x[:32])["logits"], m(x[:32])["logits"]
+    assert torch.equal(a, b)
