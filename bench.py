@@ -251,7 +251,7 @@ def run_gpu_arm(args) -> None:
     trace, ops.GEMM_TRACE = ops.GEMM_TRACE, None
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in trace)
     gemm_flops = sum(f for _, _, f in trace)
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
     ms_step = ms_total / args.steps
     value = args.gpus * BATCH * args.steps / (ms_total / 1e3)
 

@@ -8,7 +8,12 @@
 //   warp 0      TMA producer   (one thread)            global -> 4-stage smem ring, 128B swizzle
 //   warp 1      MMA issuer     (one thread)            128 x 256 x 16 tcgen05.mma, fp32 in TMEM
 //   warp 2      TMEM allocator (512 columns = 2 accumulator stages of 256 columns)
-//   warps 4..7  epilogue       (thread == output row)  tcgen05.ld -> bias/GELU/residual -> global
+//   warps 4..7  epilogue       tcgen05.ld (thread == accumulator row) -> bias/GELU/residual in
+//                              registers -> 128-byte row segments transposed through a swizzled
+//                              per-warp smem tile -> fully coalesced 128-bit global accesses
+//                              (every store instruction writes 4 complete 128 B lines). Residual /
+//                              pre-activation inputs take the same path in reverse and are
+//                              prefetched one segment ahead so their latency hides behind the MMAs.
 // The epilogue of tile i overlaps the main loop of tile i+1 through the two TMEM stages.
 #include "common.cuh"
 
@@ -22,7 +27,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 32 * 128;  // per epilogue warp: 32 rows x one 128-byte segment
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmTcParams {
   int M, N, K;
@@ -38,98 +44,232 @@ struct GemmTcParams {
   long long ldaux;
 };
 
-struct Vec8 {
-  float v[8];
+// exact-GELU pieces in ~15 instructions: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7),
+// sharing the one exponential exp(-x^2/2) between the cdf and the pdf. erff() costs ~3x as much
+// and made the fc1 / fc2-dgrad epilogues ALU-bound (4 warps vs the tensor pipe).
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-0.5f * x * x);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;           // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  pdf = 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float c, p;
+  gelu_parts(x, c, p);
+  return x * c;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float c, p;
+  gelu_parts(x, c, p);
+  return fmaf(x, p, c);
+}
+
+// ---- per-warp staging tile: 32 rows x 128 B, 16-byte units XOR-swizzled by (row & 7) -----------
+// thread-per-row accesses (lane == row) and row-coalesced accesses (8 lanes per row) are both
+// bank-conflict free.
+__device__ __forceinline__ uint4* stg_unit(uint8_t* stg, int row, int unit) {
+  return reinterpret_cast<uint4*>(stg + row * 128 + ((unit ^ (row & 7)) << 4));
+}
+
+struct SegGeom {       // one 128-byte output segment of this warp's 32 rows
+  long long row0;      // first global row of the warp
+  int col0;            // first column of the segment (elements)
+  int elem;            // bytes per element of the matrix being moved
 };
 
-__device__ __forceinline__ Vec8 load8_f32(const float* p) {
-  Vec8 r;
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float4 b = *reinterpret_cast<const float4*>(p + 4);
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-  return r;
+// global -> registers, coalesced: lane handles rows i*4 + lane/8, 16-byte unit lane%8
+template <int EPI>
+__device__ __forceinline__ void aux_prefetch(uint4 (&pre)[8], const GemmTcParams& p, const SegGeom& g,
+                                             int lane) {
+  const int upe = 16 / g.elem;  // elements per 16-byte unit
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    const int unit = (lane & 7) ^ (r & 7);  // logical unit that lives at physical slot lane&7
+    const long long row = g.row0 + r;
+    const int col = g.col0 + unit * upe;
+    pre[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (row < p.M && col < p.N) {
+      long long arow = row;
+      if (EPI == FV_EPI_PATCH) arow = row % p.tokens_per_img + 1;  // pos_embed row of this token
+      pre[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.aux) +
+                                                    (arow * p.ldaux + col) * g.elem));
+    }
+  }
 }
-__device__ __forceinline__ Vec8 load8_bf16(const __nv_bfloat16* p) {
-  Vec8 r;
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  float2 t;
-  t = unpack_bf16(u.x); r.v[0] = t.x; r.v[1] = t.y;
-  t = unpack_bf16(u.y); r.v[2] = t.x; r.v[3] = t.y;
-  t = unpack_bf16(u.z); r.v[4] = t.x; r.v[5] = t.y;
-  t = unpack_bf16(u.w); r.v[6] = t.x; r.v[7] = t.y;
-  return r;
+__device__ __forceinline__ void aux_to_stage(const uint4 (&pre)[8], uint8_t* stg, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    *reinterpret_cast<uint4*>(stg + r * 128 + ((lane & 7) << 4)) = pre[i];
+  }
 }
-__device__ __forceinline__ void store8_f32(float* p, const Vec8& r) {
-  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
-}
-__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const Vec8& r) {
-  uint4 u;
-  u.x = pack_bf16(r.v[0], r.v[1]);
-  u.y = pack_bf16(r.v[2], r.v[3]);
-  u.z = pack_bf16(r.v[4], r.v[5]);
-  u.w = pack_bf16(r.v[6], r.v[7]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-__device__ __forceinline__ void red_add8_f32(float* p, const Vec8& r) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
-               "f"(r.v[2]), "f"(r.v[3])
-               : "memory");
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "f"(r.v[4]),
-               "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
-               : "memory");
+// staging -> global, coalesced; MODE 0 store, 1 red.add.f32 (weight-gradient accumulate)
+template <int EPI>
+__device__ __forceinline__ void stage_flush(uint8_t* stg, void* base, long long ld, const GemmTcParams& p,
+                                            const SegGeom& g, int lane) {
+  const int upe = 16 / g.elem;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    const int unit = (lane & 7) ^ (r & 7);
+    const long long row = g.row0 + r;
+    const int col = g.col0 + unit * upe;
+    if (row < p.M && col < p.N) {
+      const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 128 + ((lane & 7) << 4));
+      long long orow = row;
+      if (EPI == FV_EPI_PATCH) orow = row + row / p.tokens_per_img + 1;  // row 0 of each image is cls
+      uint8_t* dst = reinterpret_cast<uint8_t*>(base) + (orow * ld + col) * g.elem;
+      if (EPI == FV_EPI_ACCUM) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(__uint_as_float(v.x)),
+                     "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                     : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(dst) = v;
+      }
+    }
+  }
 }
 
+// One 32-column chunk of this thread's row: acc (+bias) (+aux) -> packed 16-byte units in `stg`
+// (and `stg2` values for the GELU pre-activation). `mine` holds this row's aux units of the chunk.
 template <int EPI>
-__device__ __forceinline__ void epilogue_store8(const GemmTcParams& p, long long row, int col,
-                                                Vec8 acc) {
+__device__ __forceinline__ void chunk_math(float (&v)[32], const GemmTcParams& p, int col0,
+                                           const uint4* mine /*this chunk's aux units or nullptr*/) {
   if (EPI != FV_EPI_ACCUM && EPI != FV_EPI_DGELU && p.bias != nullptr) {
-    const Vec8 b = load8_f32(p.bias + col);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc.v[i] += b.v[i];
+    for (int q = 0; q < 8; ++q) {
+      if (col0 + q * 4 < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
+        v[q * 4 + 0] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+      }
+    }
   }
-  if (EPI == FV_EPI_NONE) {
-    if (p.c_bf16) store8_bf16(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, acc);
-    else store8_f32(reinterpret_cast<float*>(p.c) + row * p.ldc + col, acc);
-  } else if (EPI == FV_EPI_RESIDUAL) {
-    const Vec8 r = load8_f32(reinterpret_cast<const float*>(p.aux) + row * p.ldaux + col);
+  if (EPI == FV_EPI_RESIDUAL || EPI == FV_EPI_PATCH) {  // fp32 aux, 8 units per chunk
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc.v[i] += r.v[i];
-    store8_f32(reinterpret_cast<float*>(p.c) + row * p.ldc + col, acc);
-  } else if (EPI == FV_EPI_GELU) {
-    Vec8 g;
-    if (p.c_bf16) {
-      // the activation is computed from the *rounded* pre-activation, as autocast does
-      // (fc1 emits bf16, nn.GELU then runs on that bf16 tensor)
-      store8_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux) + row * p.ldaux + col, acc);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        g.v[i] = gelu_erf(__bfloat162float(__float2bfloat16_rn(acc.v[i])));
-      store8_bf16(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, g);
-    } else {
-      store8_f32(reinterpret_cast<float*>(p.aux) + row * p.ldaux + col, acc);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g.v[i] = gelu_erf(acc.v[i]);
-      store8_f32(reinterpret_cast<float*>(p.c) + row * p.ldc + col, g);
+    for (int q = 0; q < 8; ++q) {
+      v[q * 4 + 0] += __uint_as_float(mine[q].x); v[q * 4 + 1] += __uint_as_float(mine[q].y);
+      v[q * 4 + 2] += __uint_as_float(mine[q].z); v[q * 4 + 3] += __uint_as_float(mine[q].w);
     }
   } else if (EPI == FV_EPI_DGELU) {
-    Vec8 u;
-    if (p.c_bf16) u = load8_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * p.ldaux + col);
-    else u = load8_f32(reinterpret_cast<const float*>(p.aux) + row * p.ldaux + col);
+    if (p.c_bf16) {  // bf16 pre-activation, 4 units per chunk
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc.v[i] *= gelu_erf_grad(u.v[i]);
-    if (p.c_bf16) store8_bf16(reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.ldc + col, acc);
-    else store8_f32(reinterpret_cast<float*>(p.c) + row * p.ldc + col, acc);
-  } else if (EPI == FV_EPI_ACCUM) {
-    red_add8_f32(reinterpret_cast<float*>(p.c) + row * p.ldc + col, acc);
-  } else if (EPI == FV_EPI_PATCH) {
-    const long long img = row / p.tokens_per_img;
-    const long long tok = row - img * p.tokens_per_img + 1;  // row 0 of every image is cls
-    const Vec8 pe = load8_f32(reinterpret_cast<const float*>(p.aux) + tok * p.ldaux + col);
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {mine[q].x, mine[q].y, mine[q].z, mine[q].w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc.v[i] += pe.v[i];
-    store8_f32(reinterpret_cast<float*>(p.c) + (row + img + 1) * p.ldc + col, acc);
+        for (int j = 0; j < 4; ++j) {
+          const float2 u = unpack_bf16(w[j]);
+          v[q * 8 + j * 2] *= gelu_grad_fast(u.x);
+          v[q * 8 + j * 2 + 1] *= gelu_grad_fast(u.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        v[q * 4 + 0] *= gelu_grad_fast(__uint_as_float(mine[q].x));
+        v[q * 4 + 1] *= gelu_grad_fast(__uint_as_float(mine[q].y));
+        v[q * 4 + 2] *= gelu_grad_fast(__uint_as_float(mine[q].z));
+        v[q * 4 + 3] *= gelu_grad_fast(__uint_as_float(mine[q].w));
+      }
+    }
+  }
+}
+
+// write this thread's 32 values of a chunk into its staging row, starting at 16-byte unit `u0`
+__device__ __forceinline__ void chunk_to_stage(const float (&v)[32], uint8_t* stg, int lane, int u0,
+                                               bool bf16) {
+  if (bf16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 w;
+      w.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+      w.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+      w.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+      w.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+      *stg_unit(stg, lane, u0 + q) = w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      *stg_unit(stg, lane, u0 + q) = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
+                                                __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+    }
+  }
+}
+
+// Epilogue of one 128 x 256 accumulator tile for one warp (its 32 TMEM lanes / rows).
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* stg, uint32_t taddr,
+                                              long long row0, int n0, int lane) {
+  constexpr bool HAS_AUX_IN = (EPI == FV_EPI_RESIDUAL || EPI == FV_EPI_DGELU || EPI == FV_EPI_PATCH);
+  const bool bf16 = p.c_bf16 != 0;
+  const int seg_cols = bf16 ? 64 : 32;          // columns per 128-byte segment
+  const int chunks_per_seg = bf16 ? 2 : 1;
+  const int aux_elem = (EPI == FV_EPI_DGELU) ? (bf16 ? 2 : 4) : 4;
+  const int aux_units_per_chunk = 32 * aux_elem / 16;
+  int nseg = (p.N - n0 + seg_cols - 1) / seg_cols;
+  if (nseg > BN / seg_cols) nseg = BN / seg_cols;
+
+  uint4 pre[8];
+  SegGeom ga{row0, n0, aux_elem};
+  if (HAS_AUX_IN) aux_prefetch<EPI>(pre, p, ga, lane);
+
+  for (int s = 0; s < nseg; ++s) {
+    uint4 mine[8];
+    if (HAS_AUX_IN) {
+      // bounce the prefetched aux segment through the staging tile so each thread gets its row
+      aux_to_stage(pre, stg, lane);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mine[q] = *stg_unit(stg, lane, q);
+      __syncwarp();
+      if (s + 1 < nseg) {
+        ga.col0 = n0 + (s + 1) * seg_cols;
+        aux_prefetch<EPI>(pre, p, ga, lane);  // in flight while this segment is computed and stored
+      }
+    }
+    const SegGeom go{row0, n0 + s * seg_cols, bf16 ? 2 : 4};
+    float v2[2][32];  // GELU only: activations of the segment's chunks (pre-activations go out first)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (c < chunks_per_seg) {
+        const int col0 = go.col0 + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + (s * seg_cols + c * 32), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        chunk_math<EPI>(v, p, col0, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr);
+        chunk_to_stage(v, stg, lane, c * (bf16 ? 4 : 8), bf16);
+        if (EPI == FV_EPI_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            // the activation is computed from the *rounded* pre-activation, as autocast does
+            // (fc1 emits bf16, nn.GELU then runs on that bf16 tensor)
+            const float u = bf16 ? __bfloat162float(__float2bfloat16_rn(v[i])) : v[i];
+            v2[c][i] = gelu_fast(u);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (EPI == FV_EPI_GELU) {
+      stage_flush<EPI>(stg, p.aux, p.ldaux, p, go, lane);  // pre-activation -> aux
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        if (c < chunks_per_seg) chunk_to_stage(v2[c], stg, lane, c * (bf16 ? 4 : 8), bf16);
+      __syncwarp();
+    }
+    stage_flush<EPI>(stg, p.c, p.ldc, p, go, lane);
+    __syncwarp();
   }
 }
 
@@ -140,7 +280,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;  // 4 x 4 KiB, 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 4 * EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -258,28 +399,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int n_blk = mn - m_blk * p.num_n_blocks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const long long row = static_cast<long long>(m_blk) * BM + wq * 32 + lane;
+      const long long row0 = static_cast<long long>(m_blk) * BM + wq * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        const int col0 = n_blk * BN + chunk * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + chunk * 32, r);
-        tmem_ld_wait();
-        if (row < p.M) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              Vec8 a;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) a.v[i] = __uint_as_float(r[g * 8 + i]);
-              epilogue_store8<EPI>(p, row, col, a);
-            }
-          }
-        }
-      }
+      epilogue_tile<EPI>(p, epi_stage + wq * EPI_STAGE_BYTES, taddr, row0, n_blk * BN, lane);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

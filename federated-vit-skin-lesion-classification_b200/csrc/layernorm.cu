@@ -14,7 +14,7 @@ namespace fv {
 constexpr int LN_MAX_VEC = 8;     // float4 per lane -> D <= 1024
 constexpr int LN_WARPS = 8;       // rows per CTA pass
 
-template <bool OUT_BF16>
+template <int NV, bool OUT_BF16>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, void* __restrict__ y, float* __restrict__ mean,
@@ -24,10 +24,10 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   if (row >= rows) return;
   const int nvec = cols >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
-  float4 v[LN_MAX_VEC];
+  float4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       v[i] = __ldcs(xr + c);
@@ -37,7 +37,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   const float mu = warp_sum(s) / cols;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       const float a = v[i].x - mu, b = v[i].y - mu, d = v[i].z - mu, e = v[i].w - mu;
@@ -52,7 +52,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
@@ -75,8 +75,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 
 // Backward. Each warp walks rows with a grid stride and keeps its slice of dgamma / dbeta in
 // registers; one shared-memory reduction and one atomicAdd per column per CTA at the end.
-template <bool DY_BF16>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+template <int NV, bool DY_BF16>
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 6 ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ dres,
@@ -88,11 +88,9 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   const int warp = threadIdx.x >> 5;
   const int nvec = cols >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  float4 gam[LN_MAX_VEC], dg[LN_MAX_VEC], db[LN_MAX_VEC];
+  float4 dg[NV], db[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
-    const int c = lane + 32 * i;
-    gam[i] = c < nvec ? __ldg(g4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -101,10 +99,10 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
        row += static_cast<long long>(gridDim.x) * LN_WARPS) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
-    float4 xh[LN_MAX_VEC], gy[LN_MAX_VEC];
+    float4 xh[NV], gy[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         const float4 xv = __ldcs(xr + c);
@@ -117,8 +115,9 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
         } else {
           d = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * cols) + c);
         }
+        const float4 gm = __ldg(g4 + c);  // gamma stays L1-resident; not worth NV registers
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        gy[i] = make_float4(d.x * gam[i].x, d.y * gam[i].y, d.z * gam[i].z, d.w * gam[i].w);
+        gy[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
         dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y;
         dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
         db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
@@ -129,7 +128,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
     s1 = warp_sum(s1) * inv_cols;
     s2 = warp_sum(s2) * inv_cols;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         float4 o;
@@ -155,7 +154,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   float* red_g = red;
   float* red_b = red + LN_WARPS * cols;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       reinterpret_cast<float4*>(red_g + warp * cols)[c] = dg[i];
@@ -189,12 +188,20 @@ extern "C" int fv_layernorm_fwd(const float* x, const float* gamma, const float*
   if (rows == 0) return FV_OK;
   const unsigned grid = static_cast<unsigned>(ceil_div(rows, LN_WARPS));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (y_dtype == FV_BF16)
-    layernorm_fwd_kernel<true><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows,
-                                                               (int)cols, eps);
-  else
-    layernorm_fwd_kernel<false><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, rows,
-                                                                (int)cols, eps);
+#define FV_LN_FWD(NV)                                                                              \
+  do {                                                                                             \
+    if (y_dtype == FV_BF16)                                                                        \
+      layernorm_fwd_kernel<NV, true><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, \
+                                                                     rows, (int)cols, eps);        \
+    else                                                                                           \
+      layernorm_fwd_kernel<NV, false><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, \
+                                                                      rows, (int)cols, eps);       \
+  } while (0)
+  if (cols <= 256) FV_LN_FWD(2);
+  else if (cols <= 512) FV_LN_FWD(4);
+  else if (cols <= 768) FV_LN_FWD(6);
+  else FV_LN_FWD(8);
+#undef FV_LN_FWD
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -212,26 +219,35 @@ extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, co
   FV_CHECK_ARG(dy_dtype == FV_F32 || dy_dtype == FV_BF16, "fv_layernorm_bwd: bad dy_dtype");
   if (rows == 0) return FV_OK;
   int64_t want = ceil_div(rows, LN_WARPS);
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 2;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   const size_t smem = 2 * LN_WARPS * cols * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool configured = false;
-  if (!configured) {
-    FV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * LN_MAX_VEC * 128 * 4));
-    FV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LN_WARPS * LN_MAX_VEC * 128 * 4));
-    configured = true;
-  }
-  if (dy_dtype == FV_BF16)
-    layernorm_bwd_kernel<true><<<grid, LN_WARPS * 32, smem, st>>>(
-        dy, x, gamma, mean, rstd, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_lp), dgamma, dbeta,
-        rows, (int)cols);
-  else
-    layernorm_bwd_kernel<false><<<grid, LN_WARPS * 32, smem, st>>>(
-        dy, x, gamma, mean, rstd, dres, dx, reinterpret_cast<__nv_bfloat16*>(dx_lp), dgamma, dbeta,
-        rows, (int)cols);
+  __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(dx_lp);
+#define FV_LN_BWD(NV, BF)                                                                          \
+  do {                                                                                             \
+    static bool configured = false;                                                                \
+    if (!configured) {                                                                             \
+      FV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NV, BF>,                             \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                         2 * LN_WARPS * NV * 128 * 4));                            \
+      configured = true;                                                                           \
+    }                                                                                              \
+    layernorm_bwd_kernel<NV, BF><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, \
+                                                                    dx, lp, dgamma, dbeta, rows,   \
+                                                                    (int)cols);                    \
+  } while (0)
+#define FV_LN_BWD_NV(NV)                    \
+  do {                                      \
+    if (dy_dtype == FV_BF16) FV_LN_BWD(NV, true); \
+    else FV_LN_BWD(NV, false);              \
+  } while (0)
+  if (cols <= 256) FV_LN_BWD_NV(2);
+  else if (cols <= 512) FV_LN_BWD_NV(4);
+  else if (cols <= 768) FV_LN_BWD_NV(6);
+  else FV_LN_BWD_NV(8);
+#undef FV_LN_BWD_NV
+#undef FV_LN_BWD
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

@@ -158,8 +158,10 @@ def test_flash_attention_fwd_bwd(B, N, H):
     assert rel_err(lse, torch.logsumexp(s, -1)) < 1e-5
     dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).float().view(B * N, 3, H * 64)
     ref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B * N, 3, H * 64)
+    scale_ref = float(ref.norm()) + 1e-6 * float(dout.double().norm())  # N == 1: dq, dk are exactly 0
     for i, name in enumerate("qkv"):
-        assert rel_err(dqkv[:, i], ref[:, i]) < 1e-2, name
+        err = float((dqkv[:, i].double().cpu() - ref[:, i].cpu()).norm())
+        assert err < 1e-2 * max(float(ref[:, i].norm()), 1e-3 * scale_ref), name
     # bit-reproducible (no atomics on the attention path)
     assert torch.equal(ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).view(B * N, 3, H * 64).float(), dqkv)
 
