@@ -78,14 +78,12 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&f)[4][4], const __nv_bfl
 
 // acc[16 x 64] += A(regs, 16 x 64dims) * T^T where T is a smem tile [64 rows x 64 dims]
 // (contraction over dims; the tile's rows become the accumulator's columns)
-// `npairs` (1..4): only the first npairs*16 tile rows are live (ragged last tile) — warp-uniform
 __device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (&a)[4][4],
-                                            const __nv_bfloat16* t, int lane, int npairs) {
+                                            const __nv_bfloat16* t, int lane) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
-      if (np >= npairs) break;
       uint32_t b[4];
       ldsm_x4(b, t + (np * 16 + (lane & 7) + (lane >> 4) * 8) * AT_LD + ks * 16 + ((lane >> 3) & 1) * 8);
       mma16816(acc[2 * np], a[ks], b[0], b[1]);
@@ -96,12 +94,10 @@ __device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (
 
 // acc[16 x 64dims] += P(regs, 16 x 64) * T where T is a smem tile [64 rows x 64 dims]
 // (contraction over the tile's rows)
-// `nks` (1..4): only the first nks*16 tile rows carry non-zero P (ragged last tile)
 __device__ __forceinline__ void mma_p_tile(float (&acc)[8][4], const uint32_t (&p)[4][4],
-                                           const __nv_bfloat16* t, int lane, int nks) {
+                                           const __nv_bfloat16* t, int lane) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
-    if (ks >= nks) break;
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
       uint32_t b[4];
@@ -164,7 +160,6 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const __nv_bfloat16* vb = kb + H * AT_D;
   const int nkv = (N + AT_T - 1) / AT_T;
   const float sl2 = scale * LOG2E;
-  const bool warp_live = q0 + warp * 16 < N;
 
   load_tile(sQ, qb, rs, q0, N);
   load_tile(sK[0], kb, rs, 0, N);
@@ -192,19 +187,13 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     }
     __syncthreads();
     if (j == 0) load_a_frags(qf, sQ, warp, lane);
-    if (!warp_live) {  // all 16 query rows of this warp are past the sequence end
-      __syncthreads();
-      continue;
-    }
-    const int live = min(AT_T, N - j * AT_T);
-    const int n16 = (live + 15) >> 4;
 
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) s[i][jj] = 0.f;
-    mma_a_tileT(s, qf, sK[buf], lane, n16);
+    mma_a_tileT(s, qf, sK[buf], lane);
 
     if ((j + 1) * AT_T > N) {
 #pragma unroll
@@ -245,7 +234,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     l_run[1] = l_run[1] * a1 + rsum[1];
     uint32_t pf[4][4];
     acc_to_a(pf, s);
-    mma_p_tile(o, pf, sV[buf], lane, n16);
+    mma_p_tile(o, pf, sV[buf], lane);
     __syncthreads();  // everyone is done with this K/V buffer before it is refilled
   }
 
@@ -254,7 +243,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
   }
-  const float i0 = warp_live ? 1.0f / l_run[0] : 0.f, i1 = warp_live ? 1.0f / l_run[1] : 0.f;
+  const float i0 = 1.0f / l_run[0], i1 = 1.0f / l_run[1];
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) {
     o[nb][0] *= i0; o[nb][1] *= i0;
@@ -321,7 +310,6 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   load_tile(sV[0], vb, rs, 0, N);
   cp_async_commit();
 
-  const bool warp_live = q0 + warp * 16 < N;
   // per-row softmax statistics of this thread's two rows
   const int r0 = q0 + warp * 16 + gq;
   const float* lp = lse + (static_cast<long long>(b) * H + h) * N;
@@ -355,19 +343,13 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (!warp_live) {
-      __syncthreads();
-      continue;
-    }
-    const int live = min(AT_T, N - j * AT_T);
-    const int n16 = (live + 15) >> 4;
     float s[8][4], pd[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) { s[i][jj] = 0.f; pd[i][jj] = 0.f; }
-    mma_a_tileT(s, qf, sK[buf], lane, n16);    // S  = Q K^T
-    mma_a_tileT(pd, dof, sV[buf], lane, n16);  // dP = dO V^T
+    mma_a_tileT(s, qf, sK[buf], lane);    // S  = Q K^T
+    mma_a_tileT(pd, dof, sV[buf], lane);  // dP = dO V^T
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
       const int key = j * AT_T + nb * 8 + 2 * t;
@@ -383,7 +365,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     }
     uint32_t dsf[4][4];
     acc_to_a(dsf, s);
-    mma_p_tile(dq, dsf, sK[buf], lane, n16);  // dQ += dS K
+    mma_p_tile(dq, dsf, sK[buf], lane);  // dQ += dS K
     __syncthreads();
   }
   __nv_bfloat16* dqb = dqkv + static_cast<long long>(b) * N * rs + h * AT_D;
@@ -413,7 +395,6 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   const float* dp = delta + (static_cast<long long>(b) * H + h) * N;
   const int nq = (N + AT_T - 1) / AT_T;
   const float sl2 = scale * LOG2E;
-  const bool warp_live = k0 + warp * 16 < N;
 
   // stage this CTA's K and V tiles through buffer 1, lift them into registers
   load_tile(sQ[1], kb, rs, k0, N);
@@ -456,19 +437,13 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (!warp_live) {
-      __syncthreads();
-      continue;
-    }
-    const int live = min(AT_T, N - j * AT_T);
-    const int n16 = (live + 15) >> 4;
     float st[8][4], pd[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) { st[i][jj] = 0.f; pd[i][jj] = 0.f; }
-    mma_a_tileT(st, kf, sQ[buf], lane, n16);   // S^T  = K Q^T      [16 keys x 64 queries]
-    mma_a_tileT(pd, vf, sdO[buf], lane, n16);  // dP^T = V dO^T
+    mma_a_tileT(st, kf, sQ[buf], lane);   // S^T  = K Q^T      [16 keys x 64 queries]
+    mma_a_tileT(pd, vf, sdO[buf], lane);  // dP^T = V dO^T
     uint32_t pf[4][4], dsf[4][4];
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
@@ -487,8 +462,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     }
     acc_to_a(pf, st);
     acc_to_a(dsf, pd);
-    mma_p_tile(dv, pf, sdO[buf], lane, n16);  // dV += P^T dO
-    mma_p_tile(dk, dsf, sQ[buf], lane, n16);  // dK += dS^T Q
+    mma_p_tile(dv, pf, sdO[buf], lane);  // dV += P^T dO
+    mma_p_tile(dk, dsf, sQ[buf], lane);  // dK += dS^T Q
     __syncthreads();
   }
   __nv_bfloat16* dkb = dqkv + static_cast<long long>(b) * N * rs + H * AT_D + h * AT_D;

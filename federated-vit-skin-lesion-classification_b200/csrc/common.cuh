@@ -65,8 +65,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
-  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
-  return __bfloat1622float2(t);
+  // bf16 -> fp32 is a 16-bit shift: two ALU ops, no conversion-unit traffic
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
 }
 
 // exact (erf) GELU and its derivative — what nn.GELU() (approximate='none') computes

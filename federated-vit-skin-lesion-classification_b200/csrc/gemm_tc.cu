@@ -8,7 +8,9 @@
 //   warp 0      TMA producer   (one thread)            global -> 4-stage smem ring, 128B swizzle
 //   warp 1      MMA issuer     (one thread)            128 x 256 x 16 tcgen05.mma, fp32 in TMEM
 //   warp 2      TMEM allocator (512 columns = 2 accumulator stages of 256 columns)
-//   warps 4..7  epilogue       tcgen05.ld (thread == accumulator row) -> bias/GELU/residual in
+//   warps 4..11 epilogue       (two warps per TMEM lane quarter, 128 columns each: one warp per
+//                              SMSP left the XU/FMA pipes latency-bound on the GELU epilogues)
+//                              tcgen05.ld (thread == accumulator row) -> bias/GELU/residual in
 //                              registers -> 128-byte row segments transposed through a swizzled
 //                              per-warp smem tile -> fully coalesced 128-bit global accesses
 //                              (every store instruction writes 4 complete 128 B lines). Residual /
@@ -26,9 +28,10 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // 4 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int EPI_STAGE_BYTES = 32 * 128;  // per epilogue warp: 32 rows x one 128-byte segment
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 4 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmTcParams {
   int M, N, K;
@@ -44,19 +47,31 @@ struct GemmTcParams {
   long long ldaux;
 };
 
-// exact-GELU pieces in ~15 instructions: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7),
-// sharing the one exponential exp(-x^2/2) between the cdf and the pdf. erff() costs ~3x as much
-// and made the fc1 / fc2-dgrad epilogues ALU-bound (4 warps vs the tensor pipe).
+// exact-GELU pieces in ~16 issue slots: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), sharing
+// the one exponential exp(-x^2/2) between the cdf and the pdf; the two transcendental steps are
+// single MUFU instructions (rcp.approx.ftz / ex2.approx.ftz — no range-fixup code around them).
+// erff()/__expf()/__fdividef() cost 3 MUFU + ~25 FP32 ops per element and made the fc1 / fc2-dgrad
+// epilogues XU-bound (ncu: xu pipe 55 %, tensor pipe 19 %), see profiles/.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  const float e = __expf(-0.5f * x * x);
+  const float t = rcp_ftz(fmaf(0.3275911f, z, 1.0f));
+  const float e = ex2_ftz(x * x * -0.72134752044448170368f);  // exp(-x^2/2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * e;           // erf(|x|/sqrt2)
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  const float half_erf = fmaf(poly * t, -0.5f * e, 0.5f);  // erf(|x|/sqrt2) / 2
+  cdf = 0.5f + copysignf(half_erf, x);
   pdf = 0.39894228040143267794f * e;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
@@ -206,7 +221,7 @@ __device__ __forceinline__ void chunk_to_stage(const float (&v)[32], uint8_t* st
 // Epilogue of one 128 x 256 accumulator tile for one warp (its 32 TMEM lanes / rows).
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* stg, uint32_t taddr,
-                                              long long row0, int n0, int lane) {
+                                              long long row0, int n0, int width, int lane) {
   constexpr bool HAS_AUX_IN = (EPI == FV_EPI_RESIDUAL || EPI == FV_EPI_DGELU || EPI == FV_EPI_PATCH);
   const bool bf16 = p.c_bf16 != 0;
   const int seg_cols = bf16 ? 64 : 32;          // columns per 128-byte segment
@@ -214,7 +229,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
   const int aux_elem = (EPI == FV_EPI_DGELU) ? (bf16 ? 2 : 4) : 4;
   const int aux_units_per_chunk = 32 * aux_elem / 16;
   int nseg = (p.N - n0 + seg_cols - 1) / seg_cols;
-  if (nseg > BN / seg_cols) nseg = BN / seg_cols;
+  if (nseg > width / seg_cols) nseg = width / seg_cols;
 
   uint4 pre[8];
   SegGeom ga{row0, n0, aux_elem};
@@ -235,7 +250,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
       }
     }
     const SegGeom go{row0, n0 + s * seg_cols, bf16 ? 2 : 4};
-    float v2[2][32];  // GELU only: activations of the segment's chunks (pre-activations go out first)
+    uint32_t gbuf[32];  // GELU only: the segment's activations, already packed for the store
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       if (c < chunks_per_seg) {
@@ -249,12 +264,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
         chunk_math<EPI>(v, p, col0, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr);
         chunk_to_stage(v, stg, lane, c * (bf16 ? 4 : 8), bf16);
         if (EPI == FV_EPI_GELU) {
+          // the activation is computed from the *rounded* pre-activation, as autocast does (fc1
+          // emits bf16, nn.GELU then runs on that bf16 tensor): round by packing pairs (one F2FP
+          // per two elements) and unpacking with shifts, not one F2F per element.
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            // the activation is computed from the *rounded* pre-activation, as autocast does
-            // (fc1 emits bf16, nn.GELU then runs on that bf16 tensor)
-            const float u = bf16 ? __bfloat162float(__float2bfloat16_rn(v[i])) : v[i];
-            v2[c][i] = gelu_fast(u);
+          for (int i = 0; i < 32; i += 2) {
+            if (bf16) {
+              const float2 u = unpack_bf16(pack_bf16(v[i], v[i + 1]));
+              gbuf[c * 16 + (i >> 1)] = pack_bf16(gelu_fast(u.x), gelu_fast(u.y));
+            } else {
+              gbuf[i] = __float_as_uint(gelu_fast(v[i]));
+              gbuf[i + 1] = __float_as_uint(gelu_fast(v[i + 1]));
+            }
           }
         }
       }
@@ -264,8 +285,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
       stage_flush<EPI>(stg, p.aux, p.ldaux, p, go, lane);  // pre-activation -> aux
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
-        if (c < chunks_per_seg) chunk_to_stage(v2[c], stg, lane, c * (bf16 ? 4 : 8), bf16);
+      for (int q = 0; q < 8; ++q)
+        *stg_unit(stg, lane, q) = make_uint4(gbuf[q * 4], gbuf[q * 4 + 1], gbuf[q * 4 + 2], gbuf[q * 4 + 3]);
       __syncwarp();
     }
     stage_flush<EPI>(stg, p.c, p.ldc, p, go, lane);
@@ -280,8 +301,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;  // 4 x 4 KiB, 1024-byte aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 4 * EPI_STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;  // 8 x 4 KiB, 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -301,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], EPI_WARPS * 32);
     }
     fence_mbar_init();
   }
@@ -389,7 +410,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ------------------------------- epilogue ------------------------------------------------
-    const int wq = warp - 4;  // TMEM lane quarter this warp may read (== warp % 4)
+    const int wq = warp & 3;          // TMEM lane quarter this warp may read (== warp % 4)
+    const int half = (warp - 4) >> 2;  // which 128 accumulator columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -400,8 +422,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const long long row0 = static_cast<long long>(m_blk) * BM + wq * 32;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
-      epilogue_tile<EPI>(p, epi_stage + wq * EPI_STAGE_BYTES, taddr, row0, n_blk * BN, lane);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + half * (BN / 2);
+      epilogue_tile<EPI>(p, epi_stage + (warp - 4) * EPI_STAGE_BYTES, taddr, row0,
+                         n_blk * BN + half * (BN / 2), BN / 2, lane);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
