@@ -16,6 +16,8 @@
 // are masked to -inf before the softmax and tail rows are zero-filled on load and never stored.
 // Tensor-core path: mma.sync m16n8k16 bf16 (ldmatrix-fed). This is round 1's correct baseline;
 // the tcgen05/TMEM variant replaces the two score products next.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fv {
@@ -473,6 +475,22 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   store_rows(dv, sdO[0], dvb, rs, k0, N, warp, lane);
 }
 
+// tcgen05 path for short sequences (attention_tc.cu)
+int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
+                     float scale, cudaStream_t stream);
+
+int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                     int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
+
+static bool use_tc_attention(int64_t tokens) {
+  static int forced = -1;  // FEDVIT_ATTN=legacy keeps every length on the mma.sync kernels (A/B checks)
+  if (forced < 0) {
+    const char* e = getenv("FEDVIT_ATTN");
+    forced = (e != nullptr && e[0] == 'l') ? 1 : 0;
+  }
+  return forced == 0 && tokens <= 256;
+}
+
 }  // namespace fv
 
 // fp32 instances of the attention core are composed on the host from fv_gemm_f32 (strided-batched
@@ -486,6 +504,8 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
                "fv_attention_fwd: shape out of range");
   FV_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "fv_attention_fwd: pointers must be 16-byte aligned");
+  if (use_tc_attention(tokens))
+    return attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
   dim3 grid(static_cast<unsigned>(ceil_div(tokens, AT_T)), static_cast<unsigned>(batch * heads));
   attn_fwd_kernel<<<grid, AT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse,
@@ -508,6 +528,8 @@ extern "C" int fv_attention_bwd(const void* qkv, const void* out, const void* do
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta,
       rows, (int)tokens, (int)heads);
   FV_LAUNCH_CHECK();
+  if (use_tc_attention(tokens))
+    return attention_tc_bwd(qkv, dout, lse, delta, dqkv, batch, tokens, heads, scale, st);
   dim3 grid(static_cast<unsigned>(ceil_div(tokens, AT_T)), static_cast<unsigned>(batch * heads));
   attn_bwd_dq_kernel<<<grid, AT_THREADS, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout), lse,

@@ -1,0 +1,514 @@
+// attention_tc.cu — attention core on 5th-gen tensor cores for the short ViT sequences
+// (N <= 256 tokens: 197 at 224 px), head_dim 64. Forward here; see the bottom for dispatch.
+//
+// Replaces F.scaled_dot_product_attention inside timm's Attention.forward (reference call site
+// model.py:193). One CTA per (batch, head): K/V are fetched once and the (one or two) 128-query
+// tiles run back to back. The whole key range fits one accumulator tile, so there is no
+// online-softmax rescaling at all:
+//   TMA      Q [128 x 64], K [kw x 64], V [kw x 64] straight out of timm's [B,N,3,H,64] qkv layout
+//            (3-D tensor map, rows past N zero-filled), 128B-swizzled smem
+//   MMA 1    S = Q K^T           tcgen05.mma 128 x kw x 64  -> TMEM columns [0, kw)    (fp32)
+//   softmax  thread == query row (tcgen05.ld 32x32b): row max, exp2, row sum in registers;
+//            P (bf16 pairs) is written back with tcgen05.st into TMEM columns [0, kw/2) — over the
+//            part of S this thread has already consumed — and never touches shared memory
+//   MMA 2    O = P V             tcgen05.mma, A operand from TMEM, V as an MN-major smem operand
+//                                -> TMEM columns [128, 192)
+//   epilogue O / rowsum -> bf16 -> swizzled smem transpose -> coalesced stores; LSE saved.
+// 256 TMEM columns and 80 KB smem per CTA: two CTAs per SM, so one CTA's softmax (MUFU-bound)
+// overlaps the other's MMAs.
+#include "common.cuh"
+
+namespace fv {
+
+constexpr int ATC_THREADS = 192;  // warps 0-3 softmax/epilogue, warp 4 TMA+MMA issue, warp 5 TMEM alloc
+constexpr int ATC_Q = 128;
+constexpr int ATC_KV_MAX = 256;
+constexpr int ATC_SMEM = 2 * ATC_Q * 128 + 2 * ATC_KV_MAX * 128 + 1024 + 128;
+constexpr float ATC_LOG2E = 1.4426950408889634f;
+
+struct AttnTcParams {
+  int N, H, kw;  // tokens, heads, keys rounded up to 16
+  int kv_box;    // rows of the K/V TMA box
+  float scale;
+  __nv_bfloat16* out;
+  float* lse;
+};
+
+__device__ __forceinline__ float atc_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                   const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                         // 2 x 16 KiB (both query tiles); reused as output staging
+  uint8_t* sK = sQ + 2 * ATC_Q * 128;         // 32 KiB
+  uint8_t* sV = sK + ATC_KV_MAX * 128;        // 32 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATC_KV_MAX * 128);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint64_t* bar_done = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y / p.H, h = blockIdx.y % p.H;
+  const int nqt = (p.N + ATC_Q - 1) / ATC_Q;  // 1 or 2 query tiles, processed back to back
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_done, 128);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4 && lane == 0) {
+    const int hd = p.H * 64;
+    mbar_expect_tx(bar_qk, (nqt * ATC_Q + p.kv_box) * 128);
+    for (int t = 0; t < nqt; ++t) tma_load_3d(sQ + t * ATC_Q * 128, &tmap_q, bar_qk, h * 64, t * ATC_Q, b);
+    tma_load_3d(sK, &tmap_kv, bar_qk, hd + h * 64, 0, b);
+    mbar_expect_tx(bar_v, p.kv_box * 128);
+    tma_load_3d(sV, &tmap_kv, bar_v, 2 * hd + h * 64, 0, b);
+
+    mbar_wait(bar_qk, 0);
+    const uint32_t idesc_s = make_idesc(kFmtBF16, 0, 0, ATC_Q, p.kw);
+    const uint32_t idesc_o = make_idesc(kFmtBF16, 0, 1, ATC_Q, 64);
+    const uint64_t dk = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t dv = make_smem_desc_sw128(smem_u32(sV), 64 * 128, 1024);
+    const int ksteps = p.kw >> 4;
+    for (int t = 0; t < nqt; ++t) {
+      const uint32_t ph = t & 1;
+      if (t > 0) mbar_wait(bar_done, (t - 1) & 1);  // previous tile's O has been read out of TMEM
+      tc_fence_after();
+      // S = Q K^T : both operands K-major (head dim contiguous), 4 steps of K = 16
+      const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + t * ATC_Q * 128), 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+      mbar_wait(bar_p, ph);
+      if (t == 0) mbar_wait(bar_v, 0);
+      tc_fence_after();
+      // O = P V : A = P from TMEM (16 keys = 8 packed columns per step), B = V MN-major
+      for (int k = 0; k < ksteps; ++k)
+        umma_bf16_ts(tmem + 128, tmem + k * 8, dv + k * (2048 >> 4), idesc_o, k > 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+  } else if (warp < 4) {
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const float sl2 = p.scale * ATC_LOG2E;
+    const int nchunks = (p.kw + 31) >> 5;
+    for (int t = 0; t < nqt; ++t) {
+      const uint32_t ph = t & 1;
+      const int q0 = t * ATC_Q;
+      const int q = q0 + warp * 32 + lane;
+      const bool warp_live = q0 + warp * 32 < p.N;  // warp-uniform
+      float mx = -INFINITY, sum = 0.f;
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      if (warp_live) {
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < p.N) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+        const float mxs = mx * sl2;
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t r[32], pk[16];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c * 32 + i < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs)) : 0.f;
+            const float p1 = (c * 32 + i + 1 < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs)) : 0.f;
+            sum += p0 + p1;  // fp32 row sum (the saved LSE is the exact log-sum-exp)
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x16(taddr + c * 16, pk);  // columns this thread has already consumed
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(bar_p);
+
+      mbar_wait(bar_o, ph);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (warp_live) {
+        tmem_ld_32x32(taddr + 128, o0);
+        tmem_ld_32x32(taddr + 160, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(bar_done);  // TMEM may be overwritten by the next tile's S
+      if (warp_live) {
+        const float inv = 1.0f / sum;
+        uint8_t* stg = sQ + t * ATC_Q * 128 + warp * (32 * 128);  // 32 rows x 128 B, units XOR-swizzled
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t* src = u < 4 ? &o0[u * 8] : &o1[(u - 4) * 8];
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          w.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          w.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          w.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
+        }
+        __syncwarp();
+        __nv_bfloat16* ob = p.out + (static_cast<long long>(b) * p.N * p.H + h) * 64;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          const int unit = (lane & 7) ^ (r & 7);
+          const int qq = q0 + warp * 32 + r;
+          if (qq < p.N)
+            *reinterpret_cast<uint4*>(ob + static_cast<long long>(qq) * p.H * 64 + unit * 8) =
+                *reinterpret_cast<const uint4*>(stg + r * 128 + ((lane & 7) << 4));
+        }
+        if (q < p.N) p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = mx * p.scale + logf(sum);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// 3-D map over qkv [B, N, 3*H*64] bf16: box = 64 columns x `rows` tokens x 1 image
+static int make_qkv_map(CUtensorMap* map, const void* base, int64_t batch, int64_t tokens, int64_t width,
+                        int rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return FV_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(tokens),
+                        static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(width) * 2, static_cast<cuuint64_t>(width) * tokens * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(qkv) failed (%d)", static_cast<int>(r));
+    return FV_ERR_CUDA;
+  }
+  return FV_OK;
+}
+
+int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
+                     float scale, cudaStream_t stream) {
+  AttnTcParams p;
+  p.N = static_cast<int>(tokens);
+  p.H = static_cast<int>(heads);
+  p.kw = static_cast<int>((tokens + 15) / 16 * 16);
+  p.kv_box = p.kw;
+  p.scale = scale;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  CUtensorMap mq, mkv;
+  int rc = make_qkv_map(&mq, qkv, batch, tokens, 3 * heads * 64, ATC_Q);
+  if (rc != FV_OK) return rc;
+  rc = make_qkv_map(&mkv, qkv, batch, tokens, 3 * heads * 64, p.kv_box);
+  if (rc != FV_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+    configured = true;
+  }
+  dim3 grid(1, static_cast<unsigned>(batch * heads));
+  attn_tc_fwd_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(mq, mkv, p);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward (N <= 256): one CTA per (batch, head); every product on tcgen05, accumulators in TMEM
+// ---------------------------------------------------------------------------------------------
+//   per 128-key block kb, per 128-query tile qt:
+//     MMA 1   S  = Q_qt K_kb^T  -> TMEM [0,128)        dP = dO_qt V_kb^T -> TMEM [128,256)
+//     math    (8 warps; thread == query row, half of the block's keys)
+//             P = exp2(S*scale*log2e - LSE*log2e),  dS = P * (dP - delta) * scale
+//             -> bf16, 128B-swizzled smem tiles sP / sdS  [128 queries x 128 keys]
+//     MMA 2   dV_kb += P^T dO_qt   (A = sP read MN-major)      -> TMEM [320,384)
+//             dK_kb += dS^T Q_qt   (A = sdS read MN-major)     -> TMEM [256,320)
+//             dQ_qt += dS K_kb     (A = sdS read K-major)      -> TMEM [384,448) / [448,512)
+//   dK/dV leave TMEM after the last query tile of a key block, dQ after the last key block.
+// Q / dO tiles double as A operands (K-major) and B operands (MN-major); K / V likewise — every
+// tile is loaded once per (batch, head) and nothing is transposed or re-materialised.
+constexpr int ATB_THREADS = 320;  // warps 0-7 math, warp 8 TMA+MMA issue, warp 9 TMEM alloc
+constexpr int ATB_TILE = 128 * 128;  // bytes of one [128 x 64] bf16 tile
+constexpr int ATB_SMEM = 10 * ATB_TILE + 1024 + 128;  // Q0 Q1 dO0 dO1 K V P(2) dS(2)
+
+struct AttnBwdParams {
+  int N, H, kw;
+  float scale;
+  const float* lse;
+  const float* delta;
+  __nv_bfloat16* dqkv;
+};
+
+__global__ void __launch_bounds__(ATB_THREADS, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                   const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                  // 2 tiles
+  uint8_t* sdO = sQ + 2 * ATB_TILE;    // 2 tiles
+  uint8_t* sK = sdO + 2 * ATB_TILE;
+  uint8_t* sV = sK + ATB_TILE;
+  uint8_t* sP = sV + ATB_TILE;         // 2 column blocks of 64 keys
+  uint8_t* sdS = sP + 2 * ATB_TILE;    // 2 column blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * ATB_TILE);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_kv = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_m2 = bars + 4;
+  uint64_t* bar_kvfree = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int nqt = (p.N + 127) >> 7;
+  const int nkb = (p.kw + 127) >> 7;
+  const int hd = p.H * 64;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 256);
+    mbar_init(bar_m2, 1);
+    mbar_init(bar_kvfree, 256);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t T_S = 0, T_DP = 128, T_DK = 256, T_DV = 320, T_DQ = 384;
+
+  if (warp == 8 && lane == 0) {
+    // ------------------------------ TMA + MMA issue ------------------------------------------
+    mbar_expect_tx(bar_q, nqt * 2 * ATB_TILE);
+    for (int t = 0; t < nqt; ++t) {
+      tma_load_3d(sQ + t * ATB_TILE, &tmap_qkv, bar_q, h * 64, t * 128, b);
+      tma_load_3d(sdO + t * ATB_TILE, &tmap_do, bar_q, h * 64, t * 128, b);
+    }
+    const uint32_t idesc_kk = 0;  // placeholder to keep the descriptor comments together
+    (void)idesc_kk;
+    const uint32_t id_dvk = make_idesc(kFmtBF16, 1, 1, 128, 64);  // A MN-major (P^T / dS^T), B MN-major
+    const uint32_t id_dq = make_idesc(kFmtBF16, 0, 1, 128, 64);   // A K-major (dS), B MN-major (K)
+    int it = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      if (kb > 0) mbar_wait(bar_kvfree, (kb - 1) & 1);  // dK/dV read out, K/V tiles free
+      mbar_expect_tx(bar_kv, 2 * ATB_TILE);
+      tma_load_3d(sK, &tmap_qkv, bar_kv, hd + h * 64, kb * 128, b);
+      tma_load_3d(sV, &tmap_qkv, bar_kv, 2 * hd + h * 64, kb * 128, b);
+      if (kb == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, kb & 1);
+      int kwb = p.kw - kb * 128;
+      if (kwb > 128) kwb = 128;
+      const uint32_t id_s = make_idesc(kFmtBF16, 0, 0, 128, kwb);
+      const uint64_t dK_k = make_smem_desc_sw128(smem_u32(sK), 16, 1024);        // K-major view
+      const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+      const uint64_t dK_mn = make_smem_desc_sw128(smem_u32(sK), ATB_TILE, 1024);  // MN-major view
+      for (int qt = 0; qt < nqt; ++qt, ++it) {
+        const uint64_t dQ_k = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), 16, 1024);
+        const uint64_t dO_k = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), 16, 1024);
+        const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), ATB_TILE, 1024);
+        const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), ATB_TILE, 1024);
+        tc_fence_after();
+        // MMA 1: scores and dP for this (query tile, key block); contraction over the 64 head dims
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_S, dQ_k + k * 2, dK_k + k * 2, id_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_DP, dO_k + k * 2, dV_k + k * 2, id_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, it & 1);  // P / dS tiles written
+        tc_fence_after();
+        // MMA 2: contraction over the 128 queries (dV, dK) and over the block's keys (dQ)
+        const uint64_t dP_mn = make_smem_desc_sw128(smem_u32(sP), ATB_TILE, 1024);
+        const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), ATB_TILE, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem + T_DV, dP_mn + k * 128, dO_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem + T_DK, dS_mn + k * 128, dQ_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+        const int ks = kwb >> 4;
+        for (int k = 0; k < ks; ++k) {
+          const uint64_t dS_k = make_smem_desc_sw128(smem_u32(sdS + (k >> 2) * ATB_TILE) + (k & 3) * 32, 16, 1024);
+          umma_bf16(tmem + T_DQ + qt * 64, dS_k, dK_mn + k * 128, id_dq, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_m2);
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------ math + output warps ----------------------------------------
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int r = quarter * 32 + lane;  // row inside the 128-row tile (TMEM lane)
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float sl2 = p.scale * ATC_LOG2E;
+    const float* lse_bh = p.lse + (static_cast<long long>(b) * p.H + h) * p.N;
+    const float* del_bh = p.delta + (static_cast<long long>(b) * p.H + h) * p.N;
+    uint8_t* stg = sP + warp * 4096;  // output staging (sP is idle whenever it is used)
+    const long long rs = 3LL * hd;
+    __nv_bfloat16* g_bh = p.dqkv + static_cast<long long>(b) * p.N * rs + h * 64;
+
+    // store this warp's 32 rows x 64 bf16 (TMEM columns [col, col+64) scaled by 1) to dqkv slot `slot`
+    auto store_rows = [&](uint32_t col, int slot, int row0) {
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(lane_base + col, o0);
+      tmem_ld_32x32(lane_base + col + 32, o1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t* src = u < 4 ? &o0[u * 8] : &o1[(u - 4) * 8];
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
+        w.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
+        w.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
+        w.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        const int unit = (lane & 7) ^ (rr & 7);
+        const int tok = row0 + quarter * 32 + rr;
+        if (tok < p.N)
+          *reinterpret_cast<uint4*>(g_bh + static_cast<long long>(tok) * rs + slot * hd + unit * 8) =
+              *reinterpret_cast<const uint4*>(stg + rr * 128 + ((lane & 7) << 4));
+      }
+      __syncwarp();
+    };
+
+    int it = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      for (int qt = 0; qt < nqt; ++qt, ++it) {
+        const int q = qt * 128 + r;
+        const float l2 = q < p.N ? lse_bh[q] * ATC_LOG2E : INFINITY;
+        const float dl = q < p.N ? del_bh[q] : 0.f;
+        mbar_wait(bar_s, it & 1);
+        tc_fence_after();
+        uint32_t pk[2][16], dk[2][16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t s[32], d[32];
+          tmem_ld_32x32(lane_base + T_S + hf * 64 + c * 32, s);
+          tmem_ld_32x32(lane_base + T_DP + hf * 64 + c * 32, d);
+          tmem_ld_wait();
+          const int key0 = kb * 128 + hf * 64 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = 0.f, p1 = 0.f, s0 = 0.f, s1 = 0.f;
+            if (key0 + i < p.N) {
+              p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
+              s0 = p0 * (__uint_as_float(d[i]) - dl) * p.scale;
+            }
+            if (key0 + i + 1 < p.N) {
+              p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
+              s1 = p1 * (__uint_as_float(d[i + 1]) - dl) * p.scale;
+            }
+            pk[c][i >> 1] = pack_bf16(p0, p1);
+            dk[c][i >> 1] = pack_bf16(s0, s1);
+          }
+        }
+        if (it > 0) mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 no longer reads sP / sdS
+        uint8_t* prow = sP + hf * ATB_TILE + r * 128;
+        uint8_t* srow = sdS + hf * ATB_TILE + r * 128;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int unit = (c * 4 + u) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + (unit << 4)) =
+                make_uint4(pk[c][u * 4], pk[c][u * 4 + 1], pk[c][u * 4 + 2], pk[c][u * 4 + 3]);
+            *reinterpret_cast<uint4*>(srow + (unit << 4)) =
+                make_uint4(dk[c][u * 4], dk[c][u * 4 + 1], dk[c][u * 4 + 2], dk[c][u * 4 + 3]);
+          }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+        tc_fence_before();
+        mbar_arrive(bar_p);
+      }
+      // key block done: dK (warps 0-3) and dV (warps 4-7) leave TMEM
+      mbar_wait(bar_m2, (it - 1) & 1);
+      tc_fence_after();
+      store_rows(hf == 0 ? T_DK : T_DV, hf == 0 ? 1 : 2, kb * 128);
+      tc_fence_before();
+      mbar_arrive(bar_kvfree);
+    }
+    // all key blocks done: dQ of query tile `hf`
+    if (hf < nqt) {
+      tc_fence_after();
+      store_rows(T_DQ + hf * 64, 0, hf * 128);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int make_tok_map(CUtensorMap* map, const void* base, int64_t batch, int64_t tokens, int64_t width) {
+  return make_qkv_map(map, base, batch, tokens, width, 128);
+}
+
+int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                     int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream) {
+  AttnBwdParams p;
+  p.N = static_cast<int>(tokens);
+  p.H = static_cast<int>(heads);
+  p.kw = static_cast<int>((tokens + 15) / 16 * 16);
+  p.scale = scale;
+  p.lse = lse;
+  p.delta = delta;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  CUtensorMap mq, mdo;
+  int rc = make_tok_map(&mq, qkv, batch, tokens, 3 * heads * 64);
+  if (rc != FV_OK) return rc;
+  rc = make_tok_map(&mdo, dout, batch, tokens, heads * 64);
+  if (rc != FV_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM));
+    configured = true;
+  }
+  attn_tc_bwd_kernel<<<static_cast<unsigned>(batch * heads), ATB_THREADS, ATB_SMEM, stream>>>(mq, mdo, p);
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+}  // namespace fv
