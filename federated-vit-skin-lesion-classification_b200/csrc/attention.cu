@@ -479,7 +479,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
                      float scale, cudaStream_t stream);
 
-int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                      int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
 
 static bool use_tc_attention(int64_t tokens) {
@@ -523,13 +523,13 @@ extern "C" int fv_attention_bwd(const void* qkv, const void* out, const void* do
   FV_CHECK_ARG(batch > 0 && tokens > 0 && heads > 0 && batch * heads <= 65535 && tokens < (1 << 20),
                "fv_attention_bwd: shape out of range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_tc_attention(tokens))
+    return attention_tc_bwd(qkv, out, dout, lse, dqkv, batch, tokens, heads, scale, st);
   const long long rows = batch * tokens * heads;
   attn_delta_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta,
       rows, (int)tokens, (int)heads);
   FV_LAUNCH_CHECK();
-  if (use_tc_attention(tokens))
-    return attention_tc_bwd(qkv, dout, lse, delta, dqkv, batch, tokens, heads, scale, st);
   dim3 grid(static_cast<unsigned>(ceil_div(tokens, AT_T)), static_cast<unsigned>(batch * heads));
   attn_bwd_dq_kernel<<<grid, AT_THREADS, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout), lse,

@@ -257,11 +257,13 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
 //             dK_kb += dS^T Q_qt   (A = sdS read MN-major)     -> TMEM [256,320)
 //             dQ_qt += dS K_kb     (A = sdS read K-major)      -> TMEM [384,448) / [448,512)
 //   dK/dV leave TMEM after the last query tile of a key block, dQ after the last key block.
+//   delta = rowsum(dO * O) is computed once per (batch, head) from the O / dO smem tiles (no
+//   separate pass over HBM).
 // Q / dO tiles double as A operands (K-major) and B operands (MN-major); K / V likewise — every
 // tile is loaded once per (batch, head) and nothing is transposed or re-materialised.
 constexpr int ATB_THREADS = 320;  // warps 0-7 math, warp 8 TMA+MMA issue, warp 9 TMEM alloc
 constexpr int ATB_TILE = 128 * 128;  // bytes of one [128 x 64] bf16 tile
-constexpr int ATB_SMEM = 10 * ATB_TILE + 1024 + 128;  // Q0 Q1 dO0 dO1 K V P(2) dS(2)
+constexpr int ATB_SMEM = 12 * ATB_TILE + 1024 + 1024 + 128;  // Q0 Q1 dO0 dO1 O0 O1 K V P(2) dS(2) + delta[256]
 
 struct AttnBwdParams {
   int N, H, kw;
@@ -273,17 +275,19 @@ struct AttnBwdParams {
 
 __global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                   const AttnBwdParams p) {
+                   const __grid_constant__ CUtensorMap tmap_o, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                  // 2 tiles
   uint8_t* sdO = sQ + 2 * ATB_TILE;    // 2 tiles
-  uint8_t* sK = sdO + 2 * ATB_TILE;
+  uint8_t* sO = sdO + 2 * ATB_TILE;    // 2 tiles (forward output, only for delta = rowsum(dO * O))
+  uint8_t* sK = sO + 2 * ATB_TILE;
   uint8_t* sV = sK + ATB_TILE;
   uint8_t* sP = sV + ATB_TILE;         // 2 column blocks of 64 keys
   uint8_t* sdS = sP + 2 * ATB_TILE;    // 2 column blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * ATB_TILE);
+  float* sDelta = reinterpret_cast<float*>(sdS + 2 * ATB_TILE);  // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_kv = bars + 1;
   uint64_t* bar_s = bars + 2;
@@ -301,6 +305,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_o);
     mbar_init(bar_q, 1);
     mbar_init(bar_kv, 1);
     mbar_init(bar_s, 1);
@@ -318,10 +323,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 
   if (warp == 8 && lane == 0) {
     // ------------------------------ TMA + MMA issue ------------------------------------------
-    mbar_expect_tx(bar_q, nqt * 2 * ATB_TILE);
+    mbar_expect_tx(bar_q, nqt * 3 * ATB_TILE);
     for (int t = 0; t < nqt; ++t) {
       tma_load_3d(sQ + t * ATB_TILE, &tmap_qkv, bar_q, h * 64, t * 128, b);
       tma_load_3d(sdO + t * ATB_TILE, &tmap_do, bar_q, h * 64, t * 128, b);
+      tma_load_3d(sO + t * ATB_TILE, &tmap_o, bar_q, h * 64, t * 128, b);
     }
     const uint32_t idesc_kk = 0;  // placeholder to keep the descriptor comments together
     (void)idesc_kk;
@@ -379,7 +385,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sl2 = p.scale * ATC_LOG2E;
     const float* lse_bh = p.lse + (static_cast<long long>(b) * p.H + h) * p.N;
-    const float* del_bh = p.delta + (static_cast<long long>(b) * p.H + h) * p.N;
     uint8_t* stg = sP + warp * 4096;  // output staging (sP is idle whenever it is used)
     const long long rs = 3LL * hd;
     __nv_bfloat16* g_bh = p.dqkv + static_cast<long long>(b) * p.N * rs + h * 64;
@@ -413,12 +418,34 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       __syncwarp();
     };
 
+    // delta[q] = sum_d dO[q,d] * O[q,d] for query tile `hf`, straight from the swizzled smem tiles
+    mbar_wait(bar_q, 0);
+    if (hf < nqt) {
+      const uint8_t* orow = sO + hf * ATB_TILE + r * 128;
+      const uint8_t* grow = sdO + hf * ATB_TILE + r * 128;
+      float acc = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint4 a = *reinterpret_cast<const uint4*>(orow + ((u ^ (r & 7)) << 4));
+        const uint4 g = *reinterpret_cast<const uint4*>(grow + ((u ^ (r & 7)) << 4));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 af = unpack_bf16(aw[j]), gf = unpack_bf16(gw[j]);
+          acc = fmaf(af.x, gf.x, acc);
+          acc = fmaf(af.y, gf.y, acc);
+        }
+      }
+      sDelta[hf * 128 + r] = acc;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 math warps only
+
     int it = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       for (int qt = 0; qt < nqt; ++qt, ++it) {
         const int q = qt * 128 + r;
         const float l2 = q < p.N ? lse_bh[q] * ATC_LOG2E : INFINITY;
-        const float dl = q < p.N ? del_bh[q] : 0.f;
+        const float dl = sDelta[qt * 128 + r];
         mbar_wait(bar_s, it & 1);
         tc_fence_after();
         uint32_t pk[2][16], dk[2][16];
@@ -486,7 +513,7 @@ static int make_tok_map(CUtensorMap* map, const void* base, int64_t batch, int64
   return make_qkv_map(map, base, batch, tokens, width, 128);
 }
 
-int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                      int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream) {
   AttnBwdParams p;
   p.N = static_cast<int>(tokens);
@@ -494,19 +521,21 @@ int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, const 
   p.kw = static_cast<int>((tokens + 15) / 16 * 16);
   p.scale = scale;
   p.lse = lse;
-  p.delta = delta;
+  p.delta = nullptr;  // computed in-kernel from the O / dO tiles
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  CUtensorMap mq, mdo;
+  CUtensorMap mq, mdo, mo;
   int rc = make_tok_map(&mq, qkv, batch, tokens, 3 * heads * 64);
   if (rc != FV_OK) return rc;
   rc = make_tok_map(&mdo, dout, batch, tokens, heads * 64);
+  if (rc != FV_OK) return rc;
+  rc = make_tok_map(&mo, out, batch, tokens, heads * 64);
   if (rc != FV_OK) return rc;
   static bool configured = false;
   if (!configured) {
     FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM));
     configured = true;
   }
-  attn_tc_bwd_kernel<<<static_cast<unsigned>(batch * heads), ATB_THREADS, ATB_SMEM, stream>>>(mq, mdo, p);
+  attn_tc_bwd_kernel<<<static_cast<unsigned>(batch * heads), ATB_THREADS, ATB_SMEM, stream>>>(mq, mdo, mo, p);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

@@ -31,7 +31,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int GEMM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_STAGE_BYTES = 32 * 128;  // per epilogue warp: 32 rows x one 128-byte segment
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*colsum reduce*/;
 
 struct GemmTcParams {
   int M, N, K;
@@ -45,6 +45,7 @@ struct GemmTcParams {
   long long ldc;
   void* aux;
   long long ldaux;
+  float* colsum;  // wgrad only: += column sums of op(A) (the bias gradient), or nullptr
 };
 
 // exact-GELU pieces in ~16 issue slots: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), sharing
@@ -155,15 +156,12 @@ __device__ __forceinline__ void stage_flush(uint8_t* stg, void* base, long long 
 // One 32-column chunk of this thread's row: acc (+bias) (+aux) -> packed 16-byte units in `stg`
 // (and `stg2` values for the GELU pre-activation). `mine` holds this row's aux units of the chunk.
 template <int EPI>
-__device__ __forceinline__ void chunk_math(float (&v)[32], const GemmTcParams& p, int col0,
+__device__ __forceinline__ void chunk_math(float (&v)[32], const GemmTcParams& p, const float4 (&bv)[8],
                                            const uint4* mine /*this chunk's aux units or nullptr*/) {
-  if (EPI != FV_EPI_ACCUM && EPI != FV_EPI_DGELU && p.bias != nullptr) {
+  if (EPI != FV_EPI_ACCUM && EPI != FV_EPI_DGELU) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      if (col0 + q * 4 < p.N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
-        v[q * 4 + 0] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
-      }
+      v[q * 4 + 0] += bv[q].x; v[q * 4 + 1] += bv[q].y; v[q * 4 + 2] += bv[q].z; v[q * 4 + 3] += bv[q].w;
     }
   }
   if (EPI == FV_EPI_RESIDUAL || EPI == FV_EPI_PATCH) {  // fp32 aux, 8 units per chunk
@@ -257,11 +255,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
         const int col0 = go.col0 + c * 32;
         uint32_t r[32];
         tmem_ld_32x32(taddr + (s * seg_cols + c * 32), r);
+        // the chunk's 32 bias values (a broadcast read) are fetched while the TMEM load is in flight
+        float4 bv[8];
+        if (EPI != FV_EPI_ACCUM && EPI != FV_EPI_DGELU) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            bv[q] = (p.bias != nullptr && col0 + q * 4 < p.N)
+                        ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        chunk_math<EPI>(v, p, col0, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr);
+        chunk_math<EPI>(v, p, bv, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr);
         chunk_to_stage(v, stg, lane, c * (bf16 ? 4 : 8), bf16);
         if (EPI == FV_EPI_GELU) {
           // the activation is computed from the *rounded* pre-activation, as autocast does (fc1
@@ -318,7 +325,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      // in bias-gradient mode the epilogue warps also read the A tiles: 1 MMA commit + 8 warp arrivals
+      mbar_init(&empty_bar[s], p.colsum != nullptr ? 1 + EPI_WARPS : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -414,11 +422,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int half = (warp - 4) >> 2;  // which 128 accumulator columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cs_stage = 0;
+    uint32_t cs_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
+      if (EPI == FV_EPI_ACCUM && p.colsum != nullptr) {
+        // Bias gradient fused into the weight-gradient GEMM: while the tensor core consumes the
+        // dY tiles (A operand, MN-major: [64 token rows x 128 output columns] per stage, two
+        // 128B-swizzled boxes), the otherwise idle epilogue warps add up their columns. Thread ->
+        // (column pair = tid % 64, 16-token group = tid / 64): 16 conflict-free 32-bit smem reads
+        // per stage. Only the n_blk == 0 CTA of each row block contributes; every CTA follows the
+        // same full/empty protocol.
+        const int et = threadIdx.x - 128;
+        const int cp = et & 63, rg = et >> 6;  // column pair (2 bf16 = one 32-bit word), 16-row group
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        float cs0 = 0.f, cs1 = 0.f;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (lane == 0) mbar_wait(&full_bar[cs_stage], cs_phase);  // one poller per warp
+          __syncwarp();
+          if (n_blk == 0) {
+            const uint8_t* sa = smem + cs_stage * STAGE_BYTES + (cp >> 5) * (64 * BK * 2) + (cp & 3) * 4;
+            const int unit = (cp & 31) >> 2;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const int k = rg * 16 + rr;
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(sa + k * 128 + ((unit ^ (k & 7)) << 4));
+              cs0 += __uint_as_float(w << 16);
+              cs1 += __uint_as_float(w & 0xFFFF0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[cs_stage]);
+          if (++cs_stage == STAGES) { cs_stage = 0; cs_phase ^= 1; }
+        }
+        if (n_blk == 0) {
+          float* red = reinterpret_cast<float*>(tmem_slot + 8);  // 128 floats after the barriers
+          if (et < 128) red[et] = 0.f;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          atomicAdd(&red[cp * 2], cs0);
+          atomicAdd(&red[cp * 2 + 1], cs1);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et < 128) {
+            const long long gcol = static_cast<long long>(m_blk) * BM + et;
+            if (gcol < p.M) atomicAdd(p.colsum + gcol, red[et]);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const long long row0 = static_cast<long long>(m_blk) * BM + wq * 32;
@@ -495,6 +549,10 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 
 }  // namespace fv
 
+namespace fv {
+static thread_local float* g_wgrad_colsum = nullptr;
+}
+
 extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void* b, int b_major,
                             int64_t ldb, const float* bias, void* c, int c_dtype, int64_t ldc,
                             void* aux, int64_t ldaux, int64_t m, int64_t n, int64_t k, int epilogue,
@@ -543,6 +601,9 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
   p.ldc = ldc;
   p.aux = aux;
   p.ldaux = ldaux;
+  p.colsum = g_wgrad_colsum;
+  FV_CHECK_ARG(p.colsum == nullptr || (epilogue == FV_EPI_ACCUM && a_major == FV_MAJOR_MN),
+               "fv_gemm_bf16: bias-gradient fusion needs the weight-gradient mode");
 
   CUtensorMap ta, tb;
   int rc = make_operand_map(&ta, a, a_major, m, k, lda, BM);
@@ -560,4 +621,15 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
     case FV_EPI_PATCH: return launch_gemm_tc<FV_EPI_PATCH>(ta, tb, p, st);
   }
   return FV_ERR_INVALID_ARG;
+}
+
+extern "C" int fv_wgrad_bf16(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
+                             float* dbias, int64_t tokens, int64_t out_features, int64_t in_features,
+                             int split_k, void* stream) {
+  // dW[out,in] += dY^T X ; dbias[out] += column sums of dY — one kernel (see gemm_tc.cu)
+  fv::g_wgrad_colsum = dbias;
+  const int rc = fv_gemm_bf16(dy, FV_MAJOR_MN, lddy, x, FV_MAJOR_MN, ldx, nullptr, dw, FV_F32, lddw, nullptr, 0,
+                              out_features, in_features, tokens, FV_EPI_ACCUM, split_k, 0, stream);
+  fv::g_wgrad_colsum = nullptr;
+  return rc;
 }

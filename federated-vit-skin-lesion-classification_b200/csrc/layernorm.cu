@@ -73,19 +73,29 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
-// Backward. Each warp walks rows with a grid stride and keeps its slice of dgamma / dbeta in
-// registers; one shared-memory reduction and one atomicAdd per column per CTA at the end.
+// Backward. Two warps share a row (each thread owns NV float4 columns: 3 for D = 768), four rows
+// per CTA pass, grid-stride over rows. Splitting the row keeps the per-thread state (x-hat, g*dy
+// and the running dgamma / dbeta slices) near 80 registers — three CTAs per SM instead of the one
+// or two a warp-per-row layout gets — which is what an HBM-bound kernel needs. The two row
+// statistics cross the warp pair through shared memory; dgamma / dbeta are reduced over the CTA's
+// four row slots in shared memory and leave with one atomicAdd per column per CTA.
+constexpr int LNB_THREADS = 256;
+constexpr int LNB_ROWS = 4;  // rows in flight per CTA (one per warp pair)
+
 template <int NV, bool DY_BF16>
-__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 6 ? 2 : 1)
+__global__ void __launch_bounds__(LNB_THREADS, 3)
 layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_lp,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
                      int cols) {
-  extern __shared__ float red[];  // [LN_WARPS][cols] twice
+  extern __shared__ float red[];       // [2][LNB_ROWS][cols] for the final dgamma / dbeta reduction
+  __shared__ float2 stat[LNB_ROWS][2];  // per warp pair: partial (s1, s2) of each warp
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int slot = warp >> 1;            // row slot of this warp pair
+  const int t64 = threadIdx.x & 63;      // thread index inside the pair
   const int nvec = cols >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   float4 dg[NV], db[NV];
@@ -95,77 +105,93 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float inv_cols = 1.0f / cols;
-  for (long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp; row < rows;
-       row += static_cast<long long>(gridDim.x) * LN_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
-    const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+  const long long stride = static_cast<long long>(gridDim.x) * LNB_ROWS;
+  const long long first = static_cast<long long>(blockIdx.x) * LNB_ROWS;
+  // every warp runs the same number of passes (the CTA-wide barriers below need that)
+  for (long long base = first; base < rows; base += stride) {
+    const long long row = base + slot;
+    const bool live = row < rows;
     float4 xh[NV], gy[NV];
     float s1 = 0.f, s2 = 0.f;
+    float mu = 0.f, rs = 0.f;
+    if (live) {
+      mu = mean[row];
+      rs = rstd[row];
+      const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
-        const float4 xv = __ldcs(xr + c);
-        float4 d;
-        if (DY_BF16) {
-          const uint2 pk = __ldcs(
-              reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + row * cols) + c);
-          const float2 lo = unpack_bf16(pk.x), hi = unpack_bf16(pk.y);
-          d = make_float4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-          d = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * cols) + c);
-        }
-        const float4 gm = __ldg(g4 + c);  // gamma stays L1-resident; not worth NV registers
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        gy[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y;
-        dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
-        s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
-        s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
-      }
-    }
-    s1 = warp_sum(s1) * inv_cols;
-    s2 = warp_sum(s2) * inv_cols;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
-        float4 o;
-        o.x = rs * (gy[i].x - s1 - xh[i].x * s2);
-        o.y = rs * (gy[i].y - s1 - xh[i].y * s2);
-        o.z = rs * (gy[i].z - s1 - xh[i].z * s2);
-        o.w = rs * (gy[i].w - s1 - xh[i].w * s2);
-        if (dres != nullptr) {
-          const float4 r = __ldcs(reinterpret_cast<const float4*>(dres + row * cols) + c);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
-        reinterpret_cast<float4*>(dx + row * cols)[c] = o;
-        if (dx_lp != nullptr) {
-          uint2 pk;
-          pk.x = pack_bf16(o.x, o.y);
-          pk.y = pack_bf16(o.z, o.w);
-          reinterpret_cast<uint2*>(dx_lp + row * cols)[c] = pk;
+      for (int i = 0; i < NV; ++i) {
+        const int c = t64 + 64 * i;
+        if (c < nvec) {
+          const float4 xv = __ldcs(xr + c);
+          float4 d;
+          if (DY_BF16) {
+            const uint2 pk = __ldcs(
+                reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + row * cols) + c);
+            const float2 lo = unpack_bf16(pk.x), hi = unpack_bf16(pk.y);
+            d = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            d = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * cols) + c);
+          }
+          const float4 gm = __ldg(g4 + c);
+          xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+          gy[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+          dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y;
+          dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+          db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+          s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+          s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
         }
       }
     }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) stat[slot][warp & 1] = make_float2(s1, s2);
+    __syncthreads();
+    const float2 a = stat[slot][0], b2 = stat[slot][1];
+    s1 = (a.x + b2.x) * inv_cols;
+    s2 = (a.y + b2.y) * inv_cols;
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = t64 + 64 * i;
+        if (c < nvec) {
+          float4 o;
+          o.x = rs * (gy[i].x - s1 - xh[i].x * s2);
+          o.y = rs * (gy[i].y - s1 - xh[i].y * s2);
+          o.z = rs * (gy[i].z - s1 - xh[i].z * s2);
+          o.w = rs * (gy[i].w - s1 - xh[i].w * s2);
+          if (dres != nullptr) {
+            const float4 r = __ldcs(reinterpret_cast<const float4*>(dres + row * cols) + c);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          }
+          reinterpret_cast<float4*>(dx + row * cols)[c] = o;
+          if (dx_lp != nullptr) {
+            uint2 pk;
+            pk.x = pack_bf16(o.x, o.y);
+            pk.y = pack_bf16(o.z, o.w);
+            reinterpret_cast<uint2*>(dx_lp + row * cols)[c] = pk;
+          }
+        }
+      }
+    }
+    __syncthreads();  // stat[] is rewritten by the next pass
   }
-  // CTA reduction of the per-warp dgamma / dbeta slices
+  // CTA reduction of the four row slots' dgamma / dbeta slices
   float* red_g = red;
-  float* red_b = red + LN_WARPS * cols;
+  float* red_b = red + LNB_ROWS * cols;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = lane + 32 * i;
+    const int c = t64 + 64 * i;
     if (c < nvec) {
-      reinterpret_cast<float4*>(red_g + warp * cols)[c] = dg[i];
-      reinterpret_cast<float4*>(red_b + warp * cols)[c] = db[i];
+      reinterpret_cast<float4*>(red_g + slot * cols)[c] = dg[i];
+      reinterpret_cast<float4*>(red_b + slot * cols)[c] = db[i];
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     float sg = 0.f, sb = 0.f;
 #pragma unroll
-    for (int w = 0; w < LN_WARPS; ++w) {
+    for (int w = 0; w < LNB_ROWS; ++w) {
       sg += red_g[w * cols + c];
       sb += red_b[w * cols + c];
     }
@@ -218,34 +244,24 @@ extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, co
                LN_MAX_VEC * 128);
   FV_CHECK_ARG(dy_dtype == FV_F32 || dy_dtype == FV_BF16, "fv_layernorm_bwd: bad dy_dtype");
   if (rows == 0) return FV_OK;
-  int64_t want = ceil_div(rows, LN_WARPS);
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 2;
+  int64_t want = ceil_div(rows, LNB_ROWS);
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 3;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-  const size_t smem = 2 * LN_WARPS * cols * sizeof(float);
+  const size_t smem = 2 * LNB_ROWS * cols * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(dx_lp);
-#define FV_LN_BWD(NV, BF)                                                                          \
-  do {                                                                                             \
-    static bool configured = false;                                                                \
-    if (!configured) {                                                                             \
-      FV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NV, BF>,                             \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                         2 * LN_WARPS * NV * 128 * 4));                            \
-      configured = true;                                                                           \
-    }                                                                                              \
-    layernorm_bwd_kernel<NV, BF><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres, \
-                                                                    dx, lp, dgamma, dbeta, rows,   \
-                                                                    (int)cols);                    \
-  } while (0)
-#define FV_LN_BWD_NV(NV)                    \
-  do {                                      \
+#define FV_LN_BWD(NV, BF)                                                                        \
+  layernorm_bwd_kernel<NV, BF><<<grid, LNB_THREADS, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, \
+                                                                lp, dgamma, dbeta, rows, (int)cols)
+#define FV_LN_BWD_NV(NV)                          \
+  do {                                            \
     if (dy_dtype == FV_BF16) FV_LN_BWD(NV, true); \
-    else FV_LN_BWD(NV, false);              \
+    else FV_LN_BWD(NV, false);                    \
   } while (0)
-  if (cols <= 256) FV_LN_BWD_NV(2);
-  else if (cols <= 512) FV_LN_BWD_NV(4);
-  else if (cols <= 768) FV_LN_BWD_NV(6);
-  else FV_LN_BWD_NV(8);
+  if (cols <= 256) FV_LN_BWD_NV(1);
+  else if (cols <= 512) FV_LN_BWD_NV(2);
+  else if (cols <= 768) FV_LN_BWD_NV(3);
+  else FV_LN_BWD_NV(4);
 #undef FV_LN_BWD_NV
 #undef FV_LN_BWD
   FV_LAUNCH_CHECK();

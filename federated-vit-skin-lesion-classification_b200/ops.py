@@ -132,6 +132,22 @@ def gemm_gelu(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor, pre: Te
     _gemm_impl(a, b, bias, out, pre, MAJOR_K, MAJOR_K, EPI["gelu"], 1, 0)
 
 
+@torch.library.custom_op("fedvit::wgrad", mutates_args=("dw", "dbias"))
+def wgrad(dy: Tensor, x: Tensor, dw: Tensor, dbias: Optional[Tensor], split_k: int) -> None:
+    """dw[out,in] += dy^T @ x and dbias[out] += dy.sum(0), bf16 operands, one tensor-core kernel."""
+    _need_cuda(dy, x, dw, dbias)
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dw.dtype != torch.float32:
+        raise FedVitError("wgrad: bf16 dy/x and fp32 dw required")
+    if dy.dim() != 2 or x.dim() != 2 or dy.shape[0] != x.shape[0] or dy.stride(1) != 1 or x.stride(1) != 1:
+        raise FedVitError("wgrad: dy [tokens,out], x [tokens,in] row-major")
+    if tuple(dw.shape) != (dy.shape[1], x.shape[1]) or dw.stride(1) != 1:
+        raise FedVitError("wgrad: dw must be [out, in]")
+    if dbias is not None and (dbias.dtype != torch.float32 or dbias.numel() != dy.shape[1] or not dbias.is_contiguous()):
+        raise FedVitError("wgrad: dbias must be contiguous fp32 [out]")
+    LIB.call("fv_wgrad_bf16", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
+             dw.stride(0), _ptr(dbias), dy.shape[0], dy.shape[1], x.shape[1], split_k, _stream(dy))
+
+
 @torch.library.custom_op("fedvit::bgemm_f32", mutates_args=("out",))
 def bgemm_f32(
     a: Tensor, a_strides: List[int], b: Tensor, b_strides: List[int], out: Tensor,

@@ -321,11 +321,16 @@ class VisionTransformer(nn.Module):
         """Gradients of y = x W^T + b given dy [M, out]: accumulates dW, db; returns dx (or None)."""
         M = dy.shape[0]
         out_f, in_f = lin.weight.shape
-        if lin.weight.requires_grad:
-            ops.gemm(dy, x_in, None, _grad_buffer(lin.weight), None, _MN, _MN, _E["accum"],
-                     _split_k_for(out_f, in_f, M) if lp else 1, 0)
-        if lin.bias is not None and lin.bias.requires_grad:
-            ops.colsum(dy, _grad_buffer(lin.bias), True)
+        want_b = lin.bias is not None and lin.bias.requires_grad
+        if lp and lin.weight.requires_grad:
+            # bias gradient rides along in the weight-gradient kernel (no extra pass over dy)
+            ops.wgrad(dy, x_in, _grad_buffer(lin.weight), _grad_buffer(lin.bias) if want_b else None,
+                      _split_k_for(out_f, in_f, M))
+        else:
+            if lin.weight.requires_grad:
+                ops.gemm(dy, x_in, None, _grad_buffer(lin.weight), None, _MN, _MN, _E["accum"], 1, 0)
+            if want_b:
+                ops.colsum(dy, _grad_buffer(lin.bias), True)
         if not need_dx:
             return None
         dx = torch.empty((M, in_f), device=dy.device, dtype=dy.dtype)
@@ -375,12 +380,17 @@ class VisionTransformer(nn.Module):
         proj = self.patch_embed.proj
         if proj.weight.requires_grad or proj.bias.requires_grad:
             dpatch = dy.view(B, N, D)[:, 1:].reshape(B * (N - 1), D)
-            if proj.weight.requires_grad:
+            if lp and proj.weight.requires_grad:
                 gw = _grad_buffer(proj.weight)
-                ops.gemm(dpatch, st.patches, None, gw.view(D, -1), None, _MN, _MN, _E["accum"],
-                         _split_k_for(D, gw.numel() // D, B * (N - 1)) if lp else 1, 0)
-            if proj.bias.requires_grad:
-                ops.colsum(dpatch, _grad_buffer(proj.bias), True)
+                ops.wgrad(dpatch, st.patches, gw.view(D, -1),
+                          _grad_buffer(proj.bias) if proj.bias.requires_grad else None,
+                          _split_k_for(D, gw.numel() // D, B * (N - 1)))
+            else:
+                if proj.weight.requires_grad:
+                    gw = _grad_buffer(proj.weight)
+                    ops.gemm(dpatch, st.patches, None, gw.view(D, -1), None, _MN, _MN, _E["accum"], 1, 0)
+                if proj.bias.requires_grad:
+                    ops.colsum(dpatch, _grad_buffer(proj.bias), True)
 
 
 class _VitFunction(torch.autograd.Function):

@@ -81,6 +81,14 @@ int fv_gemm_bf16(const void* a, int a_major, int64_t lda,
                  int64_t m, int64_t n, int64_t k,
                  int epilogue, int split_k, int tokens_per_img, void* stream);
 
+/* Weight gradient of y = x W^T + b in one kernel: dW[out,in] += dY^T X (split-K, fp32 atomics) and
+ * dbias[out] += column sums of dY — the epilogue warps add up the dY tiles while the tensor core
+ * consumes them, so the bias gradient costs no extra pass over HBM. dbias may be NULL.
+ *   dy [tokens, out] bf16 (lddy), x [tokens, in] bf16 (ldx), dw fp32 [out, in] (lddw).            */
+int fv_wgrad_bf16(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
+                  float* dbias, int64_t tokens, int64_t out_features, int64_t in_features,
+                  int split_k, void* stream);
+
 int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_stride, int64_t a_batch_stride,
                 const float* b, int64_t b_row_stride, int64_t b_col_stride, int64_t b_batch_stride,
                 const float* bias,

@@ -282,3 +282,20 @@ def test_elementwise_helpers():
     n0 = launch_count()
     ops.cast_bf16(a.view(-1)[: 4096], torch.empty(4096, device=DEV, dtype=torch.bfloat16))
     assert launch_count() == n0 + 1
+
+
+@pytest.mark.parametrize("tokens,out_f,in_f,sk", [(1000, 776, 328, 3), (50432, 768, 768, 8), (197 * 4, 192, 768, 1), (37, 8, 16, 1)])
+def test_wgrad_with_fused_bias_gradient(tokens, out_f, in_f, sk):
+    g = _gen(tokens + out_f)
+    dy = torch.randn(tokens, out_f, device=DEV, generator=g).bfloat16()
+    x = torch.randn(tokens, in_f, device=DEV, generator=g).bfloat16()
+    dw = torch.randn(out_f, in_f, device=DEV, generator=g)
+    db = torch.randn(out_f, device=DEV, generator=g)
+    want_w = dw.double() + dy.double().t() @ x.double()
+    want_b = db.double() + dy.double().sum(0)
+    ops.wgrad(dy, x, dw, db, sk)
+    assert rel_err(dw, want_w) < 1e-5
+    assert rel_err(db, want_b) < 1e-5
+    dw2 = torch.zeros(out_f, in_f, device=DEV)
+    ops.wgrad(dy, x, dw2, None, sk)  # without the bias gradient
+    assert rel_err(dw2, dy.double().t() @ x.double()) < 1e-5
