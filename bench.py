@@ -285,7 +285,7 @@ def run_gpu_arm(args) -> None:
 
     cfg_e2e = model_config()
     cfg_e2e["training"]["sync_loss_every_step"] = True
-    train.train_one_epoch(net, HostLoader(2), crit, opt, None, None, None, dev, cfg_e2e, 0, None)
+    train.train_one_epoch(net, HostLoader(max(args.warmup, 3)), crit, opt, None, None, None, dev, cfg_e2e, 0, None)
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -310,7 +310,9 @@ def run_gpu_arm(args) -> None:
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.gpus),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * IMG * IMG * 4 + BATCH * 8,
-                    "d2h_bytes_per_step": 4, "api": "fedvit_b200.train.train_one_epoch (pinned host batches)"},
+                    "d2h_bytes_per_step": 4,
+                    "api": "fedvit_b200.train.train_one_epoch: pinned host batches copied per step on a side stream, "
+                           "every step's loss read back to the host (one step late, pinned scalar)"},
             "gpu_launches": launches,
             "roofline": {
                 "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all epilogues)",

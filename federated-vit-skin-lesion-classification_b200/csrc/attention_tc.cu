@@ -329,8 +329,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       tma_load_3d(sdO + t * ATB_TILE, &tmap_do, bar_q, h * 64, t * 128, b);
       tma_load_3d(sO + t * ATB_TILE, &tmap_o, bar_q, h * 64, t * 128, b);
     }
-    const uint32_t idesc_kk = 0;  // placeholder to keep the descriptor comments together
-    (void)idesc_kk;
     const uint32_t id_dvk = make_idesc(kFmtBF16, 1, 1, 128, 64);  // A MN-major (P^T / dS^T), B MN-major
     const uint32_t id_dq = make_idesc(kFmtBF16, 0, 1, 128, 64);   // A K-major (dS), B MN-major (K)
     int it = 0;
@@ -347,20 +345,25 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const uint64_t dK_k = make_smem_desc_sw128(smem_u32(sK), 16, 1024);        // K-major view
       const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
       const uint64_t dK_mn = make_smem_desc_sw128(smem_u32(sK), ATB_TILE, 1024);  // MN-major view
-      for (int qt = 0; qt < nqt; ++qt, ++it) {
+      // MMA 1 of a query tile: scores and dP; contraction over the 64 head dims
+      auto issue_mma1 = [&](int qt) {
         const uint64_t dQ_k = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), 16, 1024);
         const uint64_t dO_k = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), 16, 1024);
-        const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), ATB_TILE, 1024);
-        const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), ATB_TILE, 1024);
-        tc_fence_after();
-        // MMA 1: scores and dP for this (query tile, key block); contraction over the 64 head dims
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_S, dQ_k + k * 2, dK_k + k * 2, id_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_DP, dO_k + k * 2, dV_k + k * 2, id_s, k > 0 ? 1u : 0u);
         umma_commit(bar_s);
-        mbar_wait(bar_p, it & 1);  // P / dS tiles written
+      };
+      tc_fence_after();
+      issue_mma1(0);
+      for (int qt = 0; qt < nqt; ++qt, ++it) {
+        const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), ATB_TILE, 1024);
+        const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), ATB_TILE, 1024);
+        mbar_wait(bar_p, it & 1);  // P / dS tiles written, S / dP consumed
         tc_fence_after();
+        // the next tile's scores go first so its softmax math overlaps this tile's MMA 2
+        if (qt + 1 < nqt) issue_mma1(qt + 1);
         // MMA 2: contraction over the 128 queries (dV, dK) and over the block's keys (dQ)
         const uint64_t dP_mn = make_smem_desc_sw128(smem_u32(sP), ATB_TILE, 1024);
         const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), ATB_TILE, 1024);

@@ -99,55 +99,108 @@ struct SegGeom {       // one 128-byte output segment of this warp's 32 rows
   int elem;            // bytes per element of the matrix being moved
 };
 
-// global -> registers, coalesced: lane handles rows i*4 + lane/8, 16-byte unit lane%8
+// Row-coalesced access pattern shared by the aux prefetch and the flush: lane -> (row lane/8 + 4*i,
+// physical 16-byte slot lane%8) for i = 0..7. With r = 4*i + lane/8 the swizzled logical unit is
+// (lane%8) ^ (r&7), which only depends on the parity of i — so two global pointers per lane (even /
+// odd i), each advancing by 8 rows, replace all per-iteration index arithmetic.
+struct RowWalk {
+  uint8_t* pe;       // global address of (row0 + lr,     unit ue)
+  uint8_t* po;       // global address of (row0 + lr + 4, unit uo)
+  long long step;    // bytes per 8 rows
+  int lr;            // lane / 8
+  bool ce, co;       // column predicates of the two units
+};
+template <int EPI, bool AUX_ROWS>
+__device__ __forceinline__ RowWalk make_walk(void* base, long long ld, const GemmTcParams& p, const SegGeom& g,
+                                             int lane) {
+  RowWalk w;
+  const int upe = 16 / g.elem;
+  w.lr = lane >> 3;
+  const int ue = (lane & 7) ^ w.lr, uo = ue ^ 4;
+  w.ce = g.col0 + ue * upe < p.N;
+  w.co = g.col0 + uo * upe < p.N;
+  w.step = 8 * ld * g.elem;
+  // PATCH remaps rows (aux: pos_embed row of the token; out: one cls slot per image) — that
+  // epilogue recomputes its addresses per row in the callers below, so only the plain layout here.
+  w.pe = reinterpret_cast<uint8_t*>(base) + ((g.row0 + w.lr) * ld + g.col0 + ue * upe) * g.elem;
+  w.po = reinterpret_cast<uint8_t*>(base) + ((g.row0 + w.lr + 4) * ld + g.col0 + uo * upe) * g.elem;
+  return w;
+}
+
+// global -> registers, coalesced
 template <int EPI>
 __device__ __forceinline__ void aux_prefetch(uint4 (&pre)[8], const GemmTcParams& p, const SegGeom& g,
                                              int lane) {
-  const int upe = 16 / g.elem;  // elements per 16-byte unit
+  if (EPI == FV_EPI_PATCH) {
+    const int upe = 16 / g.elem;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3);
-    const int unit = (lane & 7) ^ (r & 7);  // logical unit that lives at physical slot lane&7
-    const long long row = g.row0 + r;
-    const int col = g.col0 + unit * upe;
-    pre[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < p.M && col < p.N) {
-      long long arow = row;
-      if (EPI == FV_EPI_PATCH) arow = row % p.tokens_per_img + 1;  // pos_embed row of this token
-      pre[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.aux) +
-                                                    (arow * p.ldaux + col) * g.elem));
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      const int unit = (lane & 7) ^ (r & 7);
+      const long long row = g.row0 + r;
+      const int col = g.col0 + unit * upe;
+      pre[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row < p.M && col < p.N) {
+        const long long arow = row % p.tokens_per_img + 1;  // pos_embed row of this token
+        pre[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.aux) +
+                                                      (arow * p.ldaux + col) * g.elem));
+      }
     }
+    return;
+  }
+  const RowWalk w = make_walk<EPI, true>(p.aux, p.ldaux, p, g, lane);
+  const long long rows_left = p.M - g.row0 - w.lr;  // row (row0+lr+4*i) is valid iff 4*i < rows_left
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    pre[2 * j] = (w.ce && 8 * j < rows_left) ? __ldg(reinterpret_cast<const uint4*>(w.pe + j * w.step))
+                                             : make_uint4(0u, 0u, 0u, 0u);
+    pre[2 * j + 1] = (w.co && 8 * j + 4 < rows_left) ? __ldg(reinterpret_cast<const uint4*>(w.po + j * w.step))
+                                                     : make_uint4(0u, 0u, 0u, 0u);
   }
 }
 __device__ __forceinline__ void aux_to_stage(const uint4 (&pre)[8], uint8_t* stg, int lane) {
+  uint8_t* s0 = stg + (lane >> 3) * 128 + ((lane & 7) << 4);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3);
-    *reinterpret_cast<uint4*>(stg + r * 128 + ((lane & 7) << 4)) = pre[i];
-  }
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(s0 + i * 512) = pre[i];
 }
-// staging -> global, coalesced; MODE 0 store, 1 red.add.f32 (weight-gradient accumulate)
+// staging -> global, coalesced; store, or red.add.f32 for the weight-gradient accumulate
 template <int EPI>
 __device__ __forceinline__ void stage_flush(uint8_t* stg, void* base, long long ld, const GemmTcParams& p,
                                             const SegGeom& g, int lane) {
-  const int upe = 16 / g.elem;
+  const uint8_t* s0 = stg + (lane >> 3) * 128 + ((lane & 7) << 4);
+  if (EPI == FV_EPI_PATCH) {
+    const int upe = 16 / g.elem;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3);
-    const int unit = (lane & 7) ^ (r & 7);
-    const long long row = g.row0 + r;
-    const int col = g.col0 + unit * upe;
-    if (row < p.M && col < p.N) {
-      const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 128 + ((lane & 7) << 4));
-      long long orow = row;
-      if (EPI == FV_EPI_PATCH) orow = row + row / p.tokens_per_img + 1;  // row 0 of each image is cls
-      uint8_t* dst = reinterpret_cast<uint8_t*>(base) + (orow * ld + col) * g.elem;
-      if (EPI == FV_EPI_ACCUM) {
-        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(__uint_as_float(v.x)),
-                     "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
-                     : "memory");
-      } else {
-        *reinterpret_cast<uint4*>(dst) = v;
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      const int unit = (lane & 7) ^ (r & 7);
+      const long long row = g.row0 + r;
+      const int col = g.col0 + unit * upe;
+      if (row < p.M && col < p.N) {
+        const long long orow = row + row / p.tokens_per_img + 1;  // row 0 of each image is cls
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(base) + (orow * ld + col) * g.elem) =
+            *reinterpret_cast<const uint4*>(s0 + i * 512);
+      }
+    }
+    return;
+  }
+  const RowWalk w = make_walk<EPI, false>(base, ld, p, g, lane);
+  const long long rows_left = p.M - g.row0 - w.lr;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const bool ok = h == 0 ? (w.ce && 8 * j < rows_left) : (w.co && 8 * j + 4 < rows_left);
+      if (ok) {
+        const uint4 v = *reinterpret_cast<const uint4*>(s0 + (2 * j + h) * 512);
+        uint8_t* dst = (h == 0 ? w.pe : w.po) + j * w.step;
+        if (EPI == FV_EPI_ACCUM) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(__uint_as_float(v.x)),
+                       "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                       : "memory");
+        } else {
+          *reinterpret_cast<uint4*>(dst) = v;
+        }
       }
     }
   }

@@ -123,8 +123,13 @@ def train_one_epoch(model: nn.Module, loader, criterion, optimizer, scheduler, s
     seen = 0
     n_steps = len(loader)
     optimizer.zero_grad(set_to_none=True)
-    sync_every_step = bool(t.get("sync_loss_every_step", False))  # the reference's per-step .item()
+    # training.sync_loss_every_step: read every step's loss back to the host like the reference does
+    # (train.py:164) — but one step late, from a pinned buffer, so the device->host read of step i
+    # overlaps the kernels of step i+1 instead of draining the GPU every iteration.
+    sync_every_step = bool(t.get("sync_loss_every_step", False))
     host_loss = 0.0
+    pending = None  # (event, pinned scalar, weight) of the previous step
+    pinned = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(2)] if sync_every_step else None
     for step, batch in enumerate(_device_batches(loader, device)):
         images, labels, meta = batch["image"], batch["label"], batch.get("metadata")
         bs = images.size(0)
@@ -152,11 +157,21 @@ def train_one_epoch(model: nn.Module, loader, criterion, optimizer, scheduler, s
                 ema.update()
 
         if sync_every_step:
-            host_loss += float(loss.item()) * accum * bs
+            buf = pinned[step & 1]
+            buf.copy_(loss.detach(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                pending[0].synchronize()
+                host_loss += float(pending[1]) * pending[2]
+            pending = (ev, buf, accum * bs)
         else:
             loss_sum += loss.detach() * (accum * bs)
         seen += bs
     if sync_every_step:
+        if pending is not None:
+            pending[0].synchronize()
+            host_loss += float(pending[1]) * pending[2]
         return host_loss / max(seen, 1)
     return float(loss_sum.item()) / max(seen, 1)
 
