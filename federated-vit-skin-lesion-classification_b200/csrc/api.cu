@@ -1,5 +1,6 @@
 // api.cu — library-wide state of libfedvit: error string, launch counter, device queries.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -30,6 +31,15 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FEDVIT_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 EncodeTiledFn get_encode_tiled() {

@@ -149,6 +149,7 @@ __device__ __forceinline__ void store_rows(const float (&o)[8][4], __nv_bfloat16
 __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ lse, int N, int H, float scale) {
+  pdl_wait();
   __shared__ __align__(16) __nv_bfloat16 sQ[AT_T * AT_LD];
   __shared__ __align__(16) __nv_bfloat16 sK[2][AT_T * AT_LD];
   __shared__ __align__(16) __nv_bfloat16 sV[2][AT_T * AT_LD];
@@ -269,6 +270,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                   float* __restrict__ delta, long long rows, int N, int H) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);  // (b, n, h)
   if (row >= rows) return;
@@ -289,6 +291,7 @@ __global__ void __launch_bounds__(AT_THREADS)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o,
                    const float* __restrict__ lse, const float* __restrict__ delta,
                    __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
+  pdl_wait();
   __shared__ __align__(16) __nv_bfloat16 sK[2][AT_T * AT_LD];
   __shared__ __align__(16) __nv_bfloat16 sV[2][AT_T * AT_LD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(AT_THREADS)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o,
                     const float* __restrict__ lse, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
+  pdl_wait();
   __shared__ __align__(16) __nv_bfloat16 sQ[2][AT_T * AT_LD];
   __shared__ __align__(16) __nv_bfloat16 sdO[2][AT_T * AT_LD];
   __shared__ float sL[2][AT_T];
@@ -507,9 +511,9 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
   if (use_tc_attention(tokens))
     return attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
   dim3 grid(static_cast<unsigned>(ceil_div(tokens, AT_T)), static_cast<unsigned>(batch * heads));
-  attn_fwd_kernel<<<grid, AT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  FV_CHECK_CUDA(fv::launch_pdl(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse,
-      (int)tokens, (int)heads, scale);
+      (int)tokens, (int)heads, scale));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -526,18 +530,18 @@ extern "C" int fv_attention_bwd(const void* qkv, const void* out, const void* do
   if (use_tc_attention(tokens))
     return attention_tc_bwd(qkv, out, dout, lse, dqkv, batch, tokens, heads, scale, st);
   const long long rows = batch * tokens * heads;
-  attn_delta_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, st>>>(
+  FV_CHECK_CUDA(fv::launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(ceil_div(rows, 8))), dim3(256), 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta,
-      rows, (int)tokens, (int)heads);
+      rows, (int)tokens, (int)heads));
   FV_LAUNCH_CHECK();
   dim3 grid(static_cast<unsigned>(ceil_div(tokens, AT_T)), static_cast<unsigned>(batch * heads));
-  attn_bwd_dq_kernel<<<grid, AT_THREADS, 0, st>>>(
+  FV_CHECK_CUDA(fv::launch_pdl(attn_bwd_dq_kernel, dim3(grid), dim3(AT_THREADS), 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), (int)tokens, (int)heads, scale);
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), (int)tokens, (int)heads, scale));
   FV_LAUNCH_CHECK();
-  attn_bwd_dkv_kernel<<<grid, AT_THREADS, 0, st>>>(
+  FV_CHECK_CUDA(fv::launch_pdl(attn_bwd_dkv_kernel, dim3(grid), dim3(AT_THREADS), 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), (int)tokens, (int)heads, scale);
+      delta, reinterpret_cast<__nv_bfloat16*>(dqkv), (int)tokens, (int)heads, scale));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

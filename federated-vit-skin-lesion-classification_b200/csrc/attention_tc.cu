@@ -78,6 +78,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // nothing above touches memory another kernel produced
 
   if (warp == 4 && lane == 0) {
     const int hd = p.H * 64;
@@ -240,7 +241,7 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
     configured = true;
   }
   dim3 grid(1, static_cast<unsigned>(batch * heads));
-  attn_tc_fwd_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(mq, mkv, p);
+  FV_CHECK_CUDA(fv::launch_pdl(attn_tc_fwd_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, mq, mkv, p));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -319,6 +320,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // nothing above touches memory another kernel produced
   constexpr uint32_t T_S = 0, T_DP = 128, T_DK = 256, T_DV = 320, T_DQ = 384;
 
   if (warp == 8 && lane == 0) {
@@ -538,7 +540,7 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
     FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM));
     configured = true;
   }
-  attn_tc_bwd_kernel<<<static_cast<unsigned>(batch * heads), ATB_THREADS, ATB_SMEM, stream>>>(mq, mdo, mo, p);
+  FV_CHECK_CUDA(fv::launch_pdl(attn_tc_bwd_kernel, dim3(static_cast<unsigned>(batch * heads)), dim3(ATB_THREADS), ATB_SMEM, stream, mq, mdo, mo, p));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

@@ -13,6 +13,7 @@ template <bool OUT_BF16>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int chans,
                 int height, int width) {
+  pdl_wait();
   const int gw = width >> 4, gh = height >> 4;
   const int kdim = chans * 256;
   const long long total = static_cast<long long>(batch) * gh * gw * (kdim >> 2);
@@ -43,6 +44,7 @@ patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch
 __global__ void __launch_bounds__(256)
 cls_pos_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                int batch, long long tokens, int dim) {
+  pdl_wait();
   const int total = batch * dim;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int b = i / dim, d = i - b * dim;
@@ -55,6 +57,7 @@ template <bool IN_BF16>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ a, long long lda, float* __restrict__ out, long long rows,
               int cols, int rows_per_block) {
+  pdl_wait();
   __shared__ float2 red[8][32];
   const int col = blockIdx.x * 64 + threadIdx.x * 2;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
@@ -93,6 +96,7 @@ colsum_kernel(const void* __restrict__ a, long long lda, float* __restrict__ out
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ s, float* __restrict__ p, long long rows, int cols,
                     float scale) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -112,6 +116,7 @@ softmax_rows_kernel(const float* __restrict__ s, float* __restrict__ p, long lon
 __global__ void __launch_bounds__(256)
 softmax_rows_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp,
                         float* __restrict__ ds, long long rows, int cols, float scale) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -141,9 +146,9 @@ extern "C" int fv_patchify(const float* img, void* out, int out_dtype, int64_t b
   const unsigned grid = static_cast<unsigned>(want < cap ? (want < 1 ? 1 : want) : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_dtype == FV_BF16)
-    patchify_kernel<true><<<grid, 256, 0, st>>>(img, out, (int)batch, (int)chans, (int)height, (int)width);
+    FV_CHECK_CUDA(fv::launch_pdl(patchify_kernel<true>, dim3(grid), dim3(256), 0, st, img, out, (int)batch, (int)chans, (int)height, (int)width));
   else
-    patchify_kernel<false><<<grid, 256, 0, st>>>(img, out, (int)batch, (int)chans, (int)height, (int)width);
+    FV_CHECK_CUDA(fv::launch_pdl(patchify_kernel<false>, dim3(grid), dim3(256), 0, st, img, out, (int)batch, (int)chans, (int)height, (int)width));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -154,7 +159,7 @@ extern "C" int fv_cls_pos_rows(const float* cls, const float* pos, float* x, int
   FV_CHECK_ARG(cls && pos && x && batch > 0 && tokens > 0 && dim > 0 && batch * dim < (1LL << 31),
                "fv_cls_pos_rows: bad argument");
   const unsigned grid = static_cast<unsigned>(ceil_div(batch * dim, 256));
-  cls_pos_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(cls, pos, x, (int)batch, tokens, (int)dim);
+  FV_CHECK_CUDA(fv::launch_pdl(cls_pos_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), cls, pos, x, (int)batch, tokens, (int)dim));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -177,9 +182,9 @@ extern "C" int fv_colsum(const void* a, int a_dtype, int64_t lda, float* out, in
   dim3 grid(col_blocks, static_cast<unsigned>(slices));
   dim3 block(32, 8);
   if (a_dtype == FV_BF16)
-    colsum_kernel<true><<<grid, block, 0, st>>>(a, lda, out, rows, (int)cols, (int)rows_per);
+    FV_CHECK_CUDA(fv::launch_pdl(colsum_kernel<true>, dim3(grid), dim3(block), 0, st, a, lda, out, rows, (int)cols, (int)rows_per));
   else
-    colsum_kernel<false><<<grid, block, 0, st>>>(a, lda, out, rows, (int)cols, (int)rows_per);
+    FV_CHECK_CUDA(fv::launch_pdl(colsum_kernel<false>, dim3(grid), dim3(block), 0, st, a, lda, out, rows, (int)cols, (int)rows_per));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -189,8 +194,8 @@ extern "C" int fv_softmax_rows(const float* s, float* p, int64_t rows, int64_t c
   using namespace fv;
   FV_CHECK_ARG(s && p && rows >= 0 && cols > 0 && cols < (1LL << 30), "fv_softmax_rows: bad argument");
   if (rows == 0) return FV_OK;
-  softmax_rows_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      s, p, rows, (int)cols, scale);
+  FV_CHECK_CUDA(fv::launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(ceil_div(rows, 8))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      s, p, rows, (int)cols, scale));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -201,8 +206,8 @@ extern "C" int fv_softmax_rows_bwd(const float* p, const float* dp, float* ds, i
   FV_CHECK_ARG(p && dp && ds && rows >= 0 && cols > 0 && cols < (1LL << 30),
                "fv_softmax_rows_bwd: bad argument");
   if (rows == 0) return FV_OK;
-  softmax_rows_bwd_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, dp, ds, rows, (int)cols, scale);
+  FV_CHECK_CUDA(fv::launch_pdl(softmax_rows_bwd_kernel, dim3(static_cast<unsigned>(ceil_div(rows, 8))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      p, dp, ds, rows, (int)cols, scale));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

@@ -27,6 +27,7 @@ struct SimtParams {
 template <int EPI>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const SimtParams p) {
+  pdl_wait();
   __shared__ float As[SM_BK][SM_BM + 4];
   __shared__ float Bs[SM_BK][SM_BN + 4];
   const int tid = threadIdx.x;
@@ -133,12 +134,12 @@ extern "C" int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_s
             static_cast<unsigned>(batch));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epilogue) {
-    case FV_EPI_NONE: gemm_simt_kernel<FV_EPI_NONE><<<grid, 256, 0, st>>>(p); break;
-    case FV_EPI_RESIDUAL: gemm_simt_kernel<FV_EPI_RESIDUAL><<<grid, 256, 0, st>>>(p); break;
-    case FV_EPI_GELU: gemm_simt_kernel<FV_EPI_GELU><<<grid, 256, 0, st>>>(p); break;
-    case FV_EPI_DGELU: gemm_simt_kernel<FV_EPI_DGELU><<<grid, 256, 0, st>>>(p); break;
-    case FV_EPI_ACCUM: gemm_simt_kernel<FV_EPI_ACCUM><<<grid, 256, 0, st>>>(p); break;
-    case FV_EPI_PATCH: gemm_simt_kernel<FV_EPI_PATCH><<<grid, 256, 0, st>>>(p); break;
+    case FV_EPI_NONE: FV_CHECK_CUDA(fv::launch_pdl(gemm_simt_kernel<FV_EPI_NONE>, dim3(grid), dim3(256), 0, st, p)); break;
+    case FV_EPI_RESIDUAL: FV_CHECK_CUDA(fv::launch_pdl(gemm_simt_kernel<FV_EPI_RESIDUAL>, dim3(grid), dim3(256), 0, st, p)); break;
+    case FV_EPI_GELU: FV_CHECK_CUDA(fv::launch_pdl(gemm_simt_kernel<FV_EPI_GELU>, dim3(grid), dim3(256), 0, st, p)); break;
+    case FV_EPI_DGELU: FV_CHECK_CUDA(fv::launch_pdl(gemm_simt_kernel<FV_EPI_DGELU>, dim3(grid), dim3(256), 0, st, p)); break;
+    case FV_EPI_ACCUM: FV_CHECK_CUDA(fv::launch_pdl(gemm_simt_kernel<FV_EPI_ACCUM>, dim3(grid), dim3(256), 0, st, p)); break;
+    case FV_EPI_PATCH: FV_CHECK_CUDA(fv::launch_pdl(gemm_simt_kernel<FV_EPI_PATCH>, dim3(grid), dim3(256), 0, st, p)); break;
   }
   FV_LAUNCH_CHECK();
   return FV_OK;

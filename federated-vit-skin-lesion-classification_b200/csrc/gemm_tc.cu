@@ -392,6 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // nothing above touches memory another kernel produced
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int total_tiles = tiles_mn * p.split_k;
@@ -595,7 +596,7 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   }
   const int total = p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, p);
+  FV_CHECK_CUDA(fv::launch_pdl(gemm_tc_kernel<EPI>, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, stream, ta, tb, p));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

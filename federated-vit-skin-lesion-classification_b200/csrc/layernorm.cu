@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, void* __restrict__ y, float* __restrict__ mean,
                      float* __restrict__ rstd, long long rows, int cols, float eps) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -90,6 +91,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_lp,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
                      int cols) {
+  pdl_wait();
   extern __shared__ float red[];       // [2][LNB_ROWS][cols] for the final dgamma / dbeta reduction
   __shared__ float2 stat[LNB_ROWS][2];  // per warp pair: partial (s1, s2) of each warp
   const int lane = threadIdx.x & 31;
@@ -217,11 +219,11 @@ extern "C" int fv_layernorm_fwd(const float* x, const float* gamma, const float*
 #define FV_LN_FWD(NV)                                                                              \
   do {                                                                                             \
     if (y_dtype == FV_BF16)                                                                        \
-      layernorm_fwd_kernel<NV, true><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, \
-                                                                     rows, (int)cols, eps);        \
+      FV_CHECK_CUDA(fv::launch_pdl(layernorm_fwd_kernel<NV, true>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y, mean, rstd, \
+                                                                     rows, (int)cols, eps));        \
     else                                                                                           \
-      layernorm_fwd_kernel<NV, false><<<grid, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y, mean, rstd, \
-                                                                      rows, (int)cols, eps);       \
+      FV_CHECK_CUDA(fv::launch_pdl(layernorm_fwd_kernel<NV, false>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y, mean, rstd, \
+                                                                      rows, (int)cols, eps));       \
   } while (0)
   if (cols <= 256) FV_LN_FWD(2);
   else if (cols <= 512) FV_LN_FWD(4);
@@ -251,8 +253,8 @@ extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, co
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(dx_lp);
 #define FV_LN_BWD(NV, BF)                                                                        \
-  layernorm_bwd_kernel<NV, BF><<<grid, LNB_THREADS, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx, \
-                                                                lp, dgamma, dbeta, rows, (int)cols)
+  FV_CHECK_CUDA(fv::launch_pdl(layernorm_bwd_kernel<NV, BF>, dim3(grid), dim3(LNB_THREADS), smem, st, dy, x, gamma, mean, rstd, dres, dx, \
+                                                                lp, dgamma, dbeta, rows, (int)cols))
 #define FV_LN_BWD_NV(NV)                          \
   do {                                            \
     if (dy_dtype == FV_BF16) FV_LN_BWD(NV, true); \

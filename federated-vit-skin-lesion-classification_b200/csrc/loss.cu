@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32)
 loss_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
             float* __restrict__ loss, float* __restrict__ dlogits, int batch, int classes,
             float gamma_neg, float gamma_pos, float clip, float eps) {
+  pdl_wait();
   __shared__ float warp_loss[LOSS_WARPS];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -101,9 +102,9 @@ extern "C" int fv_asl_loss(const float* logits, const int64_t* targets, float* l
   FV_CHECK_ARG(batch > 0 && batch < (1 << 24), "fv_asl_loss: batch=%lld out of range", (long long)batch);
   FV_CHECK_ARG(classes > 0 && classes <= 32, "fv_asl_loss: classes=%lld must be in 1..32",
                (long long)classes);
-  loss_kernel<true><<<1, LOSS_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  FV_CHECK_CUDA(fv::launch_pdl(loss_kernel<true>, dim3(1), dim3(LOSS_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 
       logits, reinterpret_cast<const long long*>(targets), loss, dlogits, (int)batch, (int)classes,
-      gamma_neg, gamma_pos, clip, eps);
+      gamma_neg, gamma_pos, clip, eps));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -115,9 +116,9 @@ extern "C" int fv_ce_loss(const float* logits, const int64_t* targets, float* lo
   FV_CHECK_ARG(batch > 0 && batch < (1 << 24), "fv_ce_loss: batch=%lld out of range", (long long)batch);
   FV_CHECK_ARG(classes > 0 && classes <= 32, "fv_ce_loss: classes=%lld must be in 1..32",
                (long long)classes);
-  loss_kernel<false><<<1, LOSS_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  FV_CHECK_CUDA(fv::launch_pdl(loss_kernel<false>, dim3(1), dim3(LOSS_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 
       logits, reinterpret_cast<const long long*>(targets), loss, dlogits, (int)batch, (int)classes,
-      0.f, 0.f, 0.f, 0.f);
+      0.f, 0.f, 0.f, 0.f));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

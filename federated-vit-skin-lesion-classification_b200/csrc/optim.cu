@@ -25,6 +25,7 @@ static inline unsigned sweep_grid(int64_t nvec, int per_thread = 4) {
 
 __global__ void __launch_bounds__(SWEEP_THREADS)
 sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  pdl_wait();
   __shared__ float red[SWEEP_THREADS / 32];
   const long long nvec = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -64,6 +65,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
              const float* __restrict__ sumsq, float max_norm, float beta1, float beta2, float eps,
              float bc1, float bc2_sqrt, float* __restrict__ ema, float ema_decay,
              __nv_bfloat16* __restrict__ p_lp, long long nvec) {
+  pdl_wait();
   __shared__ long long s_end[MAX_SEGMENTS];
   __shared__ float s_lr[MAX_SEGMENTS];
   __shared__ float s_wd[MAX_SEGMENTS];
@@ -130,6 +132,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 
 __global__ void __launch_bounds__(SWEEP_THREADS)
 scale_kernel(float* __restrict__ x, const float* __restrict__ sumsq, float max_norm, long long nvec) {
+  pdl_wait();
   const float coef = clip_coef(sumsq, max_norm);
   if (coef == 1.0f) return;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -143,6 +146,7 @@ scale_kernel(float* __restrict__ x, const float* __restrict__ sumsq, float max_n
 
 __global__ void __launch_bounds__(SWEEP_THREADS)
 ema_kernel(float* __restrict__ s, const float* __restrict__ p, float decay, long long nvec) {
+  pdl_wait();
   const float w = 1.0f - decay;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
@@ -160,6 +164,7 @@ ema_kernel(float* __restrict__ s, const float* __restrict__ p, float decay, long
 template <bool INIT>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 fedavg_kernel(float* __restrict__ acc, const float* __restrict__ w, float weight, long long nvec) {
+  pdl_wait();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += stride) {
@@ -182,6 +187,7 @@ fedavg_kernel(float* __restrict__ acc, const float* __restrict__ w, float weight
 
 __global__ void __launch_bounds__(SWEEP_THREADS)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long nvec) {
+  pdl_wait();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += stride) {
@@ -204,7 +210,7 @@ extern "C" int fv_sumsq(const float* g, int64_t n, float* sumsq, int accumulate,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!accumulate) FV_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float), st));
   if (n == 0) return FV_OK;
-  sumsq_kernel<<<sweep_grid(n >> 2, 8), SWEEP_THREADS, 0, st>>>(g, n, sumsq);
+  FV_CHECK_CUDA(fv::launch_pdl(sumsq_kernel, dim3(sweep_grid(n >> 2, 8)), dim3(SWEEP_THREADS), 0, st, g, n, sumsq));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -231,9 +237,9 @@ extern "C" int fv_adamw_flat(float* p, const float* g, float* m, float* v, const
   const long long* se = reinterpret_cast<const long long*>(seg_end);
   __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(p_lp);
 #define FV_ADAM_LAUNCH(E, L)                                                                      \
-  adamw_kernel<E, L><<<grid, SWEEP_THREADS, 0, st>>>(p, g, m, v, se, seg_lr, seg_wd, nseg, sumsq, \
+  FV_CHECK_CUDA(fv::launch_pdl(adamw_kernel<E, L>, dim3(grid), dim3(SWEEP_THREADS), 0, st, p, g, m, v, se, seg_lr, seg_wd, nseg, sumsq, \
                                                      max_norm, beta1, beta2, eps, fbc1, fbc2s,   \
-                                                     ema, ema_decay, lp, nvec)
+                                                     ema, ema_decay, lp, nvec))
   if (ema && lp) FV_ADAM_LAUNCH(true, true);
   else if (ema) FV_ADAM_LAUNCH(true, false);
   else if (lp) FV_ADAM_LAUNCH(false, true);
@@ -247,8 +253,8 @@ extern "C" int fv_scale_inplace(float* x, const float* sumsq, float max_norm, in
   using namespace fv;
   FV_CHECK_ARG(x && sumsq && n >= 0 && n % 4 == 0 && aligned16(x), "fv_scale_inplace: bad argument");
   if (n == 0) return FV_OK;
-  scale_kernel<<<sweep_grid(n >> 2), SWEEP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, sumsq, max_norm, n >> 2);
+  FV_CHECK_CUDA(fv::launch_pdl(scale_kernel, dim3(sweep_grid(n >> 2)), dim3(SWEEP_THREADS), 0, static_cast<cudaStream_t>(stream), 
+      x, sumsq, max_norm, n >> 2));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -258,8 +264,8 @@ extern "C" int fv_ema_update(float* shadow, const float* p, float decay, int64_t
   FV_CHECK_ARG(shadow && p && n >= 0 && n % 4 == 0 && aligned16(shadow) && aligned16(p),
                "fv_ema_update: bad argument");
   if (n == 0) return FV_OK;
-  ema_kernel<<<sweep_grid(n >> 2), SWEEP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      shadow, p, decay, n >> 2);
+  FV_CHECK_CUDA(fv::launch_pdl(ema_kernel, dim3(sweep_grid(n >> 2)), dim3(SWEEP_THREADS), 0, static_cast<cudaStream_t>(stream), 
+      shadow, p, decay, n >> 2));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -271,8 +277,8 @@ extern "C" int fv_fedavg_accum(float* acc, const float* w, float weight, int ini
                "fv_fedavg_accum: bad argument");
   if (n == 0) return FV_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (init) fedavg_kernel<true><<<sweep_grid(n >> 2), SWEEP_THREADS, 0, st>>>(acc, w, weight, n >> 2);
-  else fedavg_kernel<false><<<sweep_grid(n >> 2), SWEEP_THREADS, 0, st>>>(acc, w, weight, n >> 2);
+  if (init) FV_CHECK_CUDA(fv::launch_pdl(fedavg_kernel<true>, dim3(sweep_grid(n >> 2)), dim3(SWEEP_THREADS), 0, st, acc, w, weight, n >> 2));
+  else FV_CHECK_CUDA(fv::launch_pdl(fedavg_kernel<false>, dim3(sweep_grid(n >> 2)), dim3(SWEEP_THREADS), 0, st, acc, w, weight, n >> 2));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -283,8 +289,8 @@ extern "C" int fv_cast_f32_bf16(const float* src, void* dst, int64_t n, void* st
                    (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
                "fv_cast_f32_bf16: bad argument");
   if (n == 0) return FV_OK;
-  cast_bf16_kernel<<<sweep_grid(n >> 2), SWEEP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst), n >> 2);
+  FV_CHECK_CUDA(fv::launch_pdl(cast_bf16_kernel, dim3(sweep_grid(n >> 2)), dim3(SWEEP_THREADS), 0, static_cast<cudaStream_t>(stream), 
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n >> 2));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

@@ -144,8 +144,16 @@ def wgrad(dy: Tensor, x: Tensor, dw: Tensor, dbias: Optional[Tensor], split_k: i
         raise FedVitError("wgrad: dw must be [out, in]")
     if dbias is not None and (dbias.dtype != torch.float32 or dbias.numel() != dy.shape[1] or not dbias.is_contiguous()):
         raise FedVitError("wgrad: dbias must be contiguous fp32 [out]")
+    trace = GEMM_TRACE
+    if trace is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     LIB.call("fv_wgrad_bf16", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
              dw.stride(0), _ptr(dbias), dy.shape[0], dy.shape[1], x.shape[1], split_k, _stream(dy))
+    if trace is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        trace.append((e0, e1, 2.0 * dy.shape[0] * dy.shape[1] * x.shape[1]))
 
 
 @torch.library.custom_op("fedvit::bgemm_f32", mutates_args=("out",))

@@ -311,3 +311,49 @@ def test_vit_base_full_size_properties():
     with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
         a, b = m(x[:32])["logits"], m(x[:32])["logits"]
     assert torch.equal(a, b)
+
+
+def test_vit_large_384_bf16_vs_oracle():
+    """BASELINE config 4 architecture (ViT-Large/16 384 px: D=1024, L=24, H=16, N=577 — the ragged
+    long-sequence attention path) at a small batch, bf16 vs the fp32 CPU oracle."""
+    cfg = {"model": {"backbone": "vit_large_patch16_384", "num_classes": 7, "image_size": 384, "pretrained": False,
+                     "drop_path_rate": 0.0, "metadata": {"enabled": False}, "classifier": {"hidden_dim": 512, "dropout": 0.0}}}
+    torch.manual_seed(4)
+    ora = isic.model_from_config(cfg).train()
+    ours = model.build_model(cfg)
+    ours.load_state_dict(ora.state_dict())
+    ours = ours.to(DEV).train()
+    assert model.count_parameters(ours) == 304_219_143  # SURVEY.md §8.1
+    g = torch.Generator().manual_seed(1004)
+    x, y = torch.randn(2, 3, 384, 384, generator=g), torch.randint(0, 7, (2,), generator=g)
+    want_logits, want_loss, want_grads = _oracle_grads(ora, x, y)
+    FlatArena(ours)
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        logits = ours(x.to(DEV))["logits"]
+        loss = losses.AsymmetricFocalLoss()(logits, y.to(DEV))
+    loss.backward()
+    assert rel_err(logits, want_logits) < 2e-2
+    assert float(loss) == pytest.approx(want_loss, rel=2e-2)
+    worst, who = _grad_errs(ours, want_grads)
+    assert worst < 2e-2, (who, worst)
+
+
+def test_metadata_branch_and_eval_mode(golden_rgb):
+    """metadata.enabled: true (the reference default) — BatchNorm MLP + concat head on top of the
+    kernel backbone, train and eval mode, with and without the metadata tensor (zero-fill path)."""
+    cfg = micro_config()
+    cfg["model"]["metadata"] = {"enabled": True, "input_dim": 13, "hidden_dim": 32, "output_dim": 16, "dropout": 0.0}
+    torch.manual_seed(9)
+    ora = isic.model_from_config(cfg)
+    ours = model.build_model(cfg)
+    ours.load_state_dict(ora.state_dict())
+    ours = ours.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    x, meta = torch.randn(5, 3, 32, 32, generator=g), torch.rand(5, 13, generator=g)
+    for mode in ("train", "eval"):
+        getattr(ora, mode)(), getattr(ours, mode)()
+        a = ours(x.to(DEV), metadata=meta.to(DEV))["logits"]
+        b = ora(x, metadata=meta)["logits"]
+        assert rel_err(a, b) < 1e-4, mode
+    assert rel_err(ours(x.to(DEV))["logits"], ora(x)["logits"]) < 1e-4
+    assert rel_err(ours.metadata_branch.net[1].running_mean, ora.metadata_branch.net[1].running_mean) < 1e-5
