@@ -87,10 +87,10 @@ gemm_simt_kernel(const SimtParams p) {
       } else if (EPI == FV_EPI_RESIDUAL) {
         C[row * p.ldc + col] = v + p.aux[row * p.ldaux + col];
       } else if (EPI == FV_EPI_GELU) {
-        p.aux[row * p.ldaux + col] = v;
+        p.aux[row * p.ldaux + col] = gelu_erf_grad(v);  // kept for the backward instead of v itself
         C[row * p.ldc + col] = gelu_erf(v);
       } else if (EPI == FV_EPI_DGELU) {
-        C[row * p.ldc + col] = v * gelu_erf_grad(p.aux[row * p.ldaux + col]);
+        C[row * p.ldc + col] = v * p.aux[row * p.ldaux + col];
       } else if (EPI == FV_EPI_ACCUM) {
         C[row * p.ldc + col] += v;
       } else if (EPI == FV_EPI_PATCH) {

@@ -224,24 +224,24 @@ __device__ __forceinline__ void chunk_math(float (&v)[32], const GemmTcParams& p
       v[q * 4 + 2] += __uint_as_float(mine[q].z); v[q * 4 + 3] += __uint_as_float(mine[q].w);
     }
   } else if (EPI == FV_EPI_DGELU) {
-    if (p.c_bf16) {  // bf16 pre-activation, 4 units per chunk
+    if (p.c_bf16) {  // bf16 gelu'(u) saved by the forward GELU epilogue, 4 units per chunk
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t w[4] = {mine[q].x, mine[q].y, mine[q].z, mine[q].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 u = unpack_bf16(w[j]);
-          v[q * 8 + j * 2] *= gelu_grad_fast(u.x);
-          v[q * 8 + j * 2 + 1] *= gelu_grad_fast(u.y);
+          const float2 g = unpack_bf16(w[j]);
+          v[q * 8 + j * 2] *= g.x;
+          v[q * 8 + j * 2 + 1] *= g.y;
         }
       }
     } else {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        v[q * 4 + 0] *= gelu_grad_fast(__uint_as_float(mine[q].x));
-        v[q * 4 + 1] *= gelu_grad_fast(__uint_as_float(mine[q].y));
-        v[q * 4 + 2] *= gelu_grad_fast(__uint_as_float(mine[q].z));
-        v[q * 4 + 3] *= gelu_grad_fast(__uint_as_float(mine[q].w));
+        v[q * 4 + 0] *= __uint_as_float(mine[q].x);
+        v[q * 4 + 1] *= __uint_as_float(mine[q].y);
+        v[q * 4 + 2] *= __uint_as_float(mine[q].z);
+        v[q * 4 + 3] *= __uint_as_float(mine[q].w);
       }
     }
   }
@@ -322,27 +322,40 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
         chunk_math<EPI>(v, p, bv, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr);
-        chunk_to_stage(v, stg, lane, c * (bf16 ? 4 : 8), bf16);
         if (EPI == FV_EPI_GELU) {
-          // the activation is computed from the *rounded* pre-activation, as autocast does (fc1
-          // emits bf16, nn.GELU then runs on that bf16 tensor): round by packing pairs (one F2FP
-          // per two elements) and unpacking with shifts, not one F2F per element.
+          // Activation AND its derivative from the one cdf/pdf evaluation: out = u*Phi(u) goes to
+          // gbuf (stored last), aux = Phi(u) + u*phi(u) replaces the pre-activation as the tensor
+          // kept for the backward — the fc2 dgrad epilogue then only multiplies (FV_EPI_DGELU).
+          // u is first rounded to the output type, as autocast does (fc1 emits bf16 and nn.GELU
+          // runs on that tensor): round by packing pairs (one F2FP per two elements) and
+          // unpacking with shifts, not one F2F per element.
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
+            float u0 = v[i], u1 = v[i + 1];
             if (bf16) {
-              const float2 u = unpack_bf16(pack_bf16(v[i], v[i + 1]));
-              gbuf[c * 16 + (i >> 1)] = pack_bf16(gelu_fast(u.x), gelu_fast(u.y));
+              const float2 u = unpack_bf16(pack_bf16(u0, u1));
+              u0 = u.x;
+              u1 = u.y;
+            }
+            float c0, p0, c1, p1;
+            gelu_parts(u0, c0, p0);
+            gelu_parts(u1, c1, p1);
+            v[i] = fmaf(u0, p0, c0);
+            v[i + 1] = fmaf(u1, p1, c1);
+            if (bf16) {
+              gbuf[c * 16 + (i >> 1)] = pack_bf16(u0 * c0, u1 * c1);
             } else {
-              gbuf[i] = __float_as_uint(gelu_fast(v[i]));
-              gbuf[i + 1] = __float_as_uint(gelu_fast(v[i + 1]));
+              gbuf[i] = __float_as_uint(u0 * c0);
+              gbuf[i + 1] = __float_as_uint(u1 * c1);
             }
           }
         }
+        chunk_to_stage(v, stg, lane, c * (bf16 ? 4 : 8), bf16);
       }
     }
     __syncwarp();
     if (EPI == FV_EPI_GELU) {
-      stage_flush<EPI>(stg, p.aux, p.ldaux, p, go, lane);  // pre-activation -> aux
+      stage_flush<EPI>(stg, p.aux, p.ldaux, p, go, lane);  // gelu'(u) -> aux
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; ++q)

@@ -128,7 +128,11 @@ def gemm(
 
 @torch.library.custom_op("fedvit::gemm_gelu", mutates_args=("out", "pre"))
 def gemm_gelu(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor, pre: Tensor) -> None:
-    """pre = a @ b^T + bias ; out = gelu_erf(pre)  (fc1 of the MLP; both kept for the backward)."""
+    """u = a @ b^T + bias ; out = gelu_erf(u) ; pre = gelu_erf'(u)  (fc1 of the MLP).
+
+    The second output is the GELU derivative at the pre-activation, not the pre-activation itself:
+    it shares the cdf/pdf evaluation with the activation, and it is all the backward needs — the
+    fc2 dgrad epilogue (``EPI["dgelu"]``) just multiplies by it."""
     _gemm_impl(a, b, bias, out, pre, MAJOR_K, MAJOR_K, EPI["gelu"], 1, 0)
 
 

@@ -11,7 +11,7 @@ own forwards are never called. ``forward`` is one ``torch.autograd.Function`` ov
 backbone with a hand-written backward:
 
   forward  per block: LN -> qkv GEMM(+bias) -> flash attention -> proj GEMM(+bias+residual)
-                      -> LN -> fc1 GEMM(+bias, GELU, keeps pre-activation) -> fc2 GEMM(+bias+residual)
+                      -> LN -> fc1 GEMM(+bias, GELU, also emits GELU') -> fc2 GEMM(+bias+residual)
   backward per block: dgrad GEMMs (fc2's fused with GELU'), wgrad GEMMs (split-K, accumulate into
                       the fp32 gradient arena), column-sum bias grads, fused LN backward that also
                       adds the residual-path gradient and emits the bf16 copy the next GEMM reads.

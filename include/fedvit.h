@@ -41,8 +41,8 @@ extern "C" {
 /* GEMM epilogues (see fv_gemm_bf16 / fv_gemm_f32) */
 #define FV_EPI_NONE 0          /* C = acc (+bias)                                         */
 #define FV_EPI_RESIDUAL 1      /* C = acc (+bias) + R            R fp32, same shape as C   */
-#define FV_EPI_GELU 2          /* C = gelu_erf(acc+bias); C2 = acc+bias (pre-activation)   */
-#define FV_EPI_DGELU 3         /* C = acc * gelu_erf'(AUX)       AUX = saved pre-activation*/
+#define FV_EPI_GELU 2          /* u = acc+bias; C = gelu_erf(u); AUX = gelu_erf'(u) (for bwd)*/
+#define FV_EPI_DGELU 3         /* C = acc * AUX                  AUX = gelu_erf'(u) from fwd */
 #define FV_EPI_ACCUM 4         /* C (fp32) += acc                 weight-gradient accumulate*/
 #define FV_EPI_PATCH 5         /* C[row + row/tokens_per_img + 1] = acc + bias + pos[...]   */
 
@@ -66,8 +66,8 @@ int64_t fv_launch_count(void);
  *   lda/ldb         : leading dimension in elements of the stored matrix
  *   bias            : fp32 [N] or NULL
  *   c, c_dtype, ldc : output (FV_F32 or FV_BF16)
- *   aux             : FV_EPI_RESIDUAL -> fp32 residual [M,ldaux]; FV_EPI_DGELU -> pre-activation
- *                     (c_dtype) [M,ldaux]; FV_EPI_GELU -> second output (pre-activation, c_dtype);
+ *   aux             : FV_EPI_RESIDUAL -> fp32 residual [M,ldaux]; FV_EPI_GELU -> second output, the
+ *                     GELU derivative at the pre-activation (c_dtype); FV_EPI_DGELU -> that tensor;
  *                     FV_EPI_PATCH -> fp32 pos_embed [(tokens_per_img+1), N]
  *   split_k         : >1 only with FV_EPI_ACCUM: K is cut in split_k slices, each atomically
  *                     accumulated into fp32 C.

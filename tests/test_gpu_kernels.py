@@ -61,19 +61,23 @@ def test_gemm_bf16_epilogues():
     out = torch.empty(m, n, device=DEV)
     ops.gemm(a, b, bias, out, res, 0, 0, ops.EPI["residual"], 1, 0)
     assert rel_err(out, ref + bias + res) < 1e-5
-    # GELU with saved pre-activation, fp32 and bf16 stores
-    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 4e-3)):
-        o, pre = torch.empty(m, n, device=DEV, dtype=dt), torch.empty(m, n, device=DEV, dtype=dt)
-        ops.gemm_gelu(a, b, bias, o, pre)
-        assert rel_err(pre, ref + bias) < tol
-        assert rel_err(o, torch.nn.functional.gelu(pre.float())) < tol
-    # dgrad fused with GELU'
-    u = torch.randn(m, n, device=DEV, generator=g)
-    ur = u.clone().requires_grad_(True)
-    torch.nn.functional.gelu(ur).sum().backward()
+    # GELU + its derivative (kept for the backward), fp32 and bf16 stores
+    pre = (ref + bias).double().requires_grad_(True)
+    act_ref = torch.nn.functional.gelu(pre)
+    act_ref.sum().backward()
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 8e-3)):
+        o, dact = torch.empty(m, n, device=DEV, dtype=dt), torch.empty(m, n, device=DEV, dtype=dt)
+        ops.gemm_gelu(a, b, bias, o, dact)
+        assert rel_err(o, act_ref) < tol
+        assert rel_err(dact, pre.grad) < tol
+    # dgrad fused with the saved GELU derivative
+    g1 = torch.randn(m, n, device=DEV, generator=g)
     out = torch.empty(m, n, device=DEV)
-    ops.gemm(a, b, None, out, u, 0, 0, ops.EPI["dgelu"], 1, 0)
-    assert rel_err(out, ref * ur.grad) < 1e-5
+    ops.gemm(a, b, None, out, g1, 0, 0, ops.EPI["dgelu"], 1, 0)
+    assert rel_err(out, ref * g1) < 1e-5
+    outb = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, b, None, outb, g1.bfloat16(), 0, 0, ops.EPI["dgelu"], 1, 0)
+    assert rel_err(outb, ref * g1.bfloat16().float()) < 4e-3
     # accumulate + split-K
     for sk in (1, 3):
         acc = torch.randn(m, n, device=DEV, generator=g)
