@@ -301,6 +301,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// same with 64-byte swizzle (layout type 4): rows are 64 B, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr, uint32_t lbo_bytes,
+                                                        uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
 // instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate
 //   c_format [4,6)=1(F32)  a_format [7,10)  b_format [10,13)  a_major bit15  b_major bit16
 //   n>>3 [17,23)   m>>4 [24,29)

@@ -46,7 +46,34 @@ struct GemmTcParams {
   void* aux;
   long long ldaux;
   float* colsum;  // wgrad only: += column sums of op(A) (the bias gradient), or nullptr
+  // im2col-free patch embedding (FV_EPI_PATCH with im2col == 1): the A operand is the NCHW fp32
+  // image itself, fetched by a 5-D TMA map; an M tile is `ph_per_tile` rows of patches of one image
+  int im2col;
+  int gw, gh, chans;       // patch grid and input channels
+  int ph_per_tile, tiles_per_img;
 };
+
+// PATCH epilogue row mapping: local row r of M tile m_blk -> (valid?, global output row, pos row)
+__device__ __forceinline__ bool patch_row(const GemmTcParams& p, long long row0, int r, long long& orow,
+                                          long long& arow) {
+  if (p.im2col) {
+    const int m_blk = static_cast<int>(row0 / BM);  // row0 is m_blk*BM + warp quarter offset
+    const int lr = static_cast<int>(row0 - static_cast<long long>(m_blk) * BM) + r;
+    const int img = m_blk / p.tiles_per_img;
+    const int ph0 = (m_blk - img * p.tiles_per_img) * p.ph_per_tile;
+    int phs = p.gh - ph0;
+    if (phs > p.ph_per_tile) phs = p.ph_per_tile;
+    if (lr >= phs * p.gw) return false;
+    arow = static_cast<long long>(ph0) * p.gw + lr + 1;            // token index (0 is cls)
+    orow = static_cast<long long>(img) * (p.gw * p.gh + 1) + arow;
+    return true;
+  }
+  const long long row = row0 + r;
+  if (row >= p.M) return false;
+  arow = row % p.tokens_per_img + 1;          // pos_embed row of this token
+  orow = row + row / p.tokens_per_img + 1;    // row 0 of each image is cls
+  return true;
+}
 
 // exact-GELU pieces in ~16 issue slots: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), sharing
 // the one exponential exp(-x^2/2) between the cdf and the pdf; the two transcendental steps are
@@ -137,14 +164,12 @@ __device__ __forceinline__ void aux_prefetch(uint4 (&pre)[8], const GemmTcParams
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + (lane >> 3);
       const int unit = (lane & 7) ^ (r & 7);
-      const long long row = g.row0 + r;
       const int col = g.col0 + unit * upe;
+      long long orow, arow;
       pre[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (row < p.M && col < p.N) {
-        const long long arow = row % p.tokens_per_img + 1;  // pos_embed row of this token
+      if (patch_row(p, g.row0, r, orow, arow) && col < p.N)
         pre[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.aux) +
                                                       (arow * p.ldaux + col) * g.elem));
-      }
     }
     return;
   }
@@ -174,13 +199,11 @@ __device__ __forceinline__ void stage_flush(uint8_t* stg, void* base, long long 
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + (lane >> 3);
       const int unit = (lane & 7) ^ (r & 7);
-      const long long row = g.row0 + r;
       const int col = g.col0 + unit * upe;
-      if (row < p.M && col < p.N) {
-        const long long orow = row + row / p.tokens_per_img + 1;  // row 0 of each image is cls
+      long long orow, arow;
+      if (patch_row(p, g.row0, r, orow, arow) && col < p.N)
         *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(base) + (orow * ld + col) * g.elem) =
             *reinterpret_cast<const uint4*>(s0 + i * 512);
-      }
     }
     return;
   }
@@ -423,9 +446,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        mbar_expect_tx(&full_bar[stage], (EPI == FV_EPI_PATCH && p.im2col)
+                                             ? p.gw * p.ph_per_tile * 64 + BN * 64
+                                             : STAGE_BYTES);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
+        if (EPI == FV_EPI_PATCH && p.im2col) {
+          // one k-block = one pixel row of a patch: 16 fp32 = 64 B (the longest contiguous run an
+          // NCHW image offers a patch), channel kb/16, row kb%16. The box walks (px, -, pw, ph,
+          // image*channel), so the smem rows come out in token order; 64-byte swizzle.
+          const int img = m_blk / p.tiles_per_img;
+          const int ph0 = (m_blk - img * p.tiles_per_img) * p.ph_per_tile;
+          tma_load_5d(sa, &tmap_a, &full_bar[stage], 0, kb & 15, 0, ph0, img * p.chans + (kb >> 4));
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * 16, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         if (p.a_major == FV_MAJOR_K) {
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
         } else {
@@ -447,7 +483,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------- MMA issuer ---------------------------------------------
-    const uint32_t idesc = make_idesc(kFmtBF16, p.a_major, p.b_major, BM, BN);
+    const bool tf32 = (EPI == FV_EPI_PATCH) && p.im2col;
+    const uint32_t idesc = make_idesc(tf32 ? kFmtTF32 : kFmtBF16, p.a_major, p.b_major, BM, BN);
     // K-major: rows are 128 B apart, 8-row groups 1024 B apart; a K=16 step is 32 B along the row.
     // MN-major: 64-element column blocks are one [BK x 128 B] TMA box (8192 B) apart (LBO),
     //           8-k-row groups 1024 B apart (SBO); a K=16 step is 16 rows = 2048 B.
@@ -473,9 +510,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t sb = sa + A_STAGE_BYTES;
         const uint64_t da = make_smem_desc_sw128(sa, a_lbo, 1024);
         const uint64_t db = make_smem_desc_sw128(sb, b_lbo, 1024);
+        if (tf32) {  // 64-byte rows hold 16 fp32: two K = 8 steps, 32 bytes apart
+          const uint64_t da64 = make_smem_desc_sw64(sa, 16, 512);
+          const uint64_t db64 = make_smem_desc_sw64(sb, 16, 512);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          umma_bf16(tmem_d, da + k * a_kstep, db + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 2; ++k)
+            umma_tf32(tmem_d, da64 + k * 2, db64 + k * 2, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, da + k * a_kstep, db + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -669,6 +713,8 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
   p.aux = aux;
   p.ldaux = ldaux;
   p.colsum = g_wgrad_colsum;
+  p.im2col = 0;
+  p.gw = p.gh = p.chans = p.ph_per_tile = p.tiles_per_img = 0;
   FV_CHECK_ARG(p.colsum == nullptr || (epilogue == FV_EPI_ACCUM && a_major == FV_MAJOR_MN),
                "fv_gemm_bf16: bias-gradient fusion needs the weight-gradient mode");
 
@@ -699,4 +745,80 @@ extern "C" int fv_wgrad_bf16(const void* dy, int64_t lddy, const void* x, int64_
                               out_features, in_features, tokens, FV_EPI_ACCUM, split_k, 0, stream);
   fv::g_wgrad_colsum = nullptr;
   return rc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// im2col-free patch embedding: x[b, 1 + t, :] = patch(b, t) . W^T + bias + pos[1 + t]
+// -------------------------------------------------------------------------------------------------
+extern "C" int fv_patch_embed_tf32(const float* img, const float* weight, const float* bias, const float* pos,
+                                   float* x, int64_t batch, int64_t chans, int64_t height, int64_t width,
+                                   int64_t dim, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(img && weight && pos && x, "fv_patch_embed_tf32: null pointer");
+  FV_CHECK_ARG(batch > 0 && chans > 0 && height % 16 == 0 && width % 16 == 0 && height > 0 && width > 0,
+               "fv_patch_embed_tf32: H and W must be positive multiples of 16");
+  const int gw = static_cast<int>(width / 16), gh = static_cast<int>(height / 16);
+  FV_CHECK_ARG(gw <= 128 && dim % 8 == 0 && dim > 0, "fv_patch_embed_tf32: width <= 2048 px, dim %% 8 == 0");
+  FV_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0,
+               "fv_patch_embed_tf32: pointers must be 16-byte aligned");
+  EncodeTiledFn enc = get_encode_tiled();
+  FV_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  GemmTcParams p;
+  p.im2col = 1;
+  p.gw = gw;
+  p.gh = gh;
+  p.chans = static_cast<int>(chans);
+  p.ph_per_tile = BM / gw;
+  if (p.ph_per_tile > gh) p.ph_per_tile = gh;
+  p.tiles_per_img = (gh + p.ph_per_tile - 1) / p.ph_per_tile;
+  p.M = static_cast<int>(batch * gw * gh);  // logical rows (patches)
+  p.N = static_cast<int>(dim);
+  p.K = static_cast<int>(chans * 256);
+  p.num_m_blocks = static_cast<int>(batch) * p.tiles_per_img;
+  p.num_n_blocks = static_cast<int>(ceil_div(dim, BN));
+  p.num_k_blocks = static_cast<int>(chans) * 16;
+  p.split_k = 1;
+  p.kb_per_split = p.num_k_blocks;
+  p.a_major = FV_MAJOR_K;
+  p.b_major = FV_MAJOR_K;
+  p.c_bf16 = 0;
+  p.tokens_per_img = gw * gh;
+  p.bias = bias;
+  p.c = x;
+  p.ldc = dim;
+  p.aux = const_cast<float*>(pos);
+  p.ldaux = dim;
+  p.colsum = nullptr;
+
+  CUtensorMap ta, tb;
+  {  // image viewed as (px, py, pw, ph, b*c); strides in bytes for dims 1..4
+    cuuint64_t dims[5] = {16, 16, static_cast<cuuint64_t>(gw), static_cast<cuuint64_t>(gh),
+                          static_cast<cuuint64_t>(batch * chans)};
+    cuuint64_t strides[4] = {static_cast<cuuint64_t>(width) * 4, 64, static_cast<cuuint64_t>(width) * 64,
+                             static_cast<cuuint64_t>(width) * height * 4};
+    cuuint32_t box[5] = {16, 1, static_cast<cuuint32_t>(gw), static_cast<cuuint32_t>(p.ph_per_tile), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(img), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(image 5-D) failed (%d)", static_cast<int>(r));
+      return FV_ERR_CUDA;
+    }
+  }
+  {  // conv weight [dim, chans*256] fp32, K-major; 16 fp32 = one 64-byte swizzle row
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(chans * 256), static_cast<cuuint64_t>(dim)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(chans) * 256 * 4};
+    cuuint32_t box[2] = {16, BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(weight), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(patch weight) failed (%d)", static_cast<int>(r));
+      return FV_ERR_CUDA;
+    }
+  }
+  return launch_gemm_tc<FV_EPI_PATCH>(ta, tb, p, static_cast<cudaStream_t>(stream));
 }

@@ -315,6 +315,21 @@ def _(img, out_bf16):
                          dtype=torch.bfloat16 if out_bf16 else torch.float32)
 
 
+@torch.library.custom_op("fedvit::patch_embed", mutates_args=("x",))
+def patch_embed(img: Tensor, weight: Tensor, bias: Tensor, pos: Tensor, x: Tensor) -> None:
+    """Rows 1..N-1 of the residual stream from the NCHW fp32 image, im2col-free (5-D TMA, tf32)."""
+    _need_cuda(img, weight, bias, pos, x)
+    if img.dtype != torch.float32 or weight.dtype != torch.float32 or x.dtype != torch.float32:
+        raise FedVitError("patch_embed: fp32 image / weight / output")
+    img = img.contiguous()
+    b, c, h, w = img.shape
+    d = weight.shape[0]
+    if weight.numel() != d * c * 256 or not weight.is_contiguous():
+        raise FedVitError("patch_embed: weight must be a contiguous [D, C, 16, 16] conv weight")
+    LIB.call("fv_patch_embed_tf32", img.data_ptr(), weight.data_ptr(), bias.data_ptr(), pos.data_ptr(),
+             x.data_ptr(), b, c, h, w, d, _stream(img))
+
+
 @torch.library.custom_op("fedvit::cls_pos_rows", mutates_args=("x",))
 def cls_pos_rows(cls: Tensor, pos: Tensor, x: Tensor, batch: int, tokens: int, dim: int) -> None:
     _need_cuda(cls, pos, x)

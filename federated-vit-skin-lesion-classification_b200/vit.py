@@ -137,7 +137,7 @@ def _to_bf16(t: Tensor) -> Tensor:
 
 
 class _Saved:
-    __slots__ = ("lp", "B", "N", "img_shape", "patches", "blocks", "cls_rows", "meanf", "rstdf")
+    __slots__ = ("lp", "B", "N", "img", "patches", "blocks", "cls_rows", "meanf", "rstdf")
 
 
 class VisionTransformer(nn.Module):
@@ -275,10 +275,17 @@ class VisionTransformer(nn.Module):
         act = torch.bfloat16 if lp else torch.float32
         pe = self.patch_embed
 
-        patches = ops.patchify(img, lp)  # [B*(N-1), C*256]
         x = torch.empty((M, D), device=dev, dtype=torch.float32)
-        ops.gemm(patches, self._w(pe.proj.weight, lp), pe.proj.bias.detach(), x,
-                 self.pos_embed.detach().view(N, D), _K, _K, _E["patch"], 1, N - 1)
+        patches = None
+        if lp:
+            # im2col-free: the 16x16xC patches are fetched by a 5-D TMA map straight out of the NCHW
+            # image (tf32 tensor cores); nothing [B*196, C*256]-shaped is materialised in the forward
+            ops.patch_embed(img, pe.proj.weight.detach(), pe.proj.bias.detach(),
+                            self.pos_embed.detach().view(N, D), x)
+        else:
+            patches = ops.patchify(img, False)  # fp32 parity path: explicit patch rows + FFMA GEMM
+            ops.gemm(patches, self._w(pe.proj.weight, lp), pe.proj.bias.detach(), x,
+                     self.pos_embed.detach().view(N, D), _K, _K, _E["patch"], 1, N - 1)
         ops.cls_pos_rows(self.cls_token.detach(), self.pos_embed.detach(), x, B, N, D)
 
         st = None
@@ -286,6 +293,7 @@ class VisionTransformer(nn.Module):
             st = _Saved()
             st.lp, st.B, st.N = lp, B, N
             st.patches = patches
+            st.img = img
             st.blocks = []
         for blk in self.blocks:
             n1, n2, at, mlp = blk.norm1, blk.norm2, blk.attn, blk.mlp
@@ -380,6 +388,8 @@ class VisionTransformer(nn.Module):
         proj = self.patch_embed.proj
         if proj.weight.requires_grad or proj.bias.requires_grad:
             dpatch = dy.view(B, N, D)[:, 1:].reshape(B * (N - 1), D)
+            if st.patches is None:  # the forward was im2col-free; the weight gradient wants patch rows
+                st.patches = ops.patchify(st.img, lp)
             if lp and proj.weight.requires_grad:
                 gw = _grad_buffer(proj.weight)
                 ops.wgrad(dpatch, st.patches, gw.view(D, -1),

@@ -133,6 +133,16 @@ int fv_attention_bwd(const void* qkv, const void* out, const void* dout, const f
  *   fv_patchify: NCHW fp32 image -> [B*(H/16)*(W/16), C*256] rows in (c,py,px) order, bf16/fp32
  *   fv_cls_pos_rows: writes row 0 of every image: x[b,0,:] = cls + pos[0]
  * ---------------------------------------------------------------------------------------- */
+/* im2col-free patch embedding (timm PatchEmbed.proj + cls/pos prologue, rows 1..N-1):
+ *   x[b, 1 + t, :] = patch(b, t) . weight^T + bias + pos[1 + t, :]
+ * The A operand is never materialised: a 5-D TMA tensor map (px, py, pw, ph, b*c) over the NCHW
+ * fp32 image delivers [patches x 32] K-slices straight into 128B-swizzled smem in token order;
+ * tf32 tcgen05.mma, fp32 accumulate. weight is the conv weight [dim, chans, 16, 16] (fp32), pos the
+ * fp32 [N, dim] position table, x the fp32 [B*N, dim] residual stream (row 0 of each image is
+ * written by fv_cls_pos_rows).                                                                  */
+int fv_patch_embed_tf32(const float* img, const float* weight, const float* bias, const float* pos,
+                        float* x, int64_t batch, int64_t chans, int64_t height, int64_t width,
+                        int64_t dim, void* stream);
 int fv_patchify(const float* img, void* out, int out_dtype,
                 int64_t batch, int64_t chans, int64_t height, int64_t width, void* stream);
 int fv_cls_pos_rows(const float* cls, const float* pos, float* x,

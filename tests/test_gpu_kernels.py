@@ -303,3 +303,22 @@ def test_wgrad_with_fused_bias_gradient(tokens, out_f, in_f, sk):
     dw2 = torch.zeros(out_f, in_f, device=DEV)
     ops.wgrad(dy, x, dw2, None, sk)  # without the bias gradient
     assert rel_err(dw2, dy.double().t() @ x.double()) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,S,D", [(3, 3, 224, 192), (2, 4, 224, 768), (2, 3, 384, 1024), (5, 3, 32, 64)])
+def test_patch_embed_im2col_free(B, C, S, D):
+    """5-D TMA + tf32 tensor-core patch embedding vs conv2d (fp32): rows 1..N-1 get conv + bias + pos,
+    row 0 of every image is left alone; tf32 keeps 10 mantissa bits -> ~1e-3."""
+    g = _gen(S + D)
+    img = torch.randn(B, C, S, S, device=DEV, generator=g)
+    w = torch.randn(D, C, 16, 16, device=DEV, generator=g) * 0.05
+    bias = torch.randn(D, device=DEV, generator=g)
+    N = (S // 16) ** 2 + 1
+    pos = torch.randn(N, D, device=DEV, generator=g)
+    x = torch.full((B * N, D), 7.0, device=DEV)
+    ops.patch_embed(img, w, bias, pos, x)
+    ref = torch.nn.functional.conv2d(img.double(), w.double(), bias.double(), stride=16).flatten(2).transpose(1, 2)
+    ref = ref + pos[1:].double()
+    got = x.view(B, N, D)
+    assert rel_err(got[:, 1:], ref) < 2e-3
+    assert float((got[:, 0] - 7.0).abs().max()) == 0.0
