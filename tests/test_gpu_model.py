@@ -357,3 +357,24 @@ def test_metadata_branch_and_eval_mode(golden_rgb):
         assert rel_err(a, b) < 1e-4, mode
     assert rel_err(ours(x.to(DEV))["logits"], ora(x)["logits"]) < 1e-4
     assert rel_err(ours.metadata_branch.net[1].running_mean, ora.metadata_branch.net[1].running_mean) < 1e-5
+
+
+def test_graphed_eval_forward_matches_eager():
+    """CUDA-graph replay of the eval forward (config 5's launch-bound small batches) is bit-identical
+    to the eager launch sequence, and new inputs flow through the captured graph."""
+    from fedvit_b200.graphs import GraphedForward
+
+    _, ora, ours, x, y = _tiny_pair(seed=3, batch=4)
+    FlatArena(ours)
+    ours.eval()
+    xd = x.to(DEV)
+    with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        eager = ours(xd)["logits"].clone()
+    fwd = GraphedForward(ours, xd)
+    assert torch.equal(fwd(xd), eager)
+    x2 = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(77)).to(DEV)
+    with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        eager2 = ours(x2)["logits"].clone()
+    assert torch.equal(fwd(x2), eager2)
+    with pytest.raises(ValueError):
+        fwd(x2[:2])

@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-batch", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--graph", action="store_true", help="replay the forward as one CUDA graph per batch size")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
@@ -35,19 +36,26 @@ def main():
     b = 1
     while b <= args.max_batch:
         x = torch.randn(b, 3, 224, 224, device=dev)
+        if args.graph:
+            from fedvit_b200.graphs import GraphedForward
+
+            fwd = GraphedForward(net, x)
+            run = lambda: fwd(x).argmax(1)
+        else:
+            run = lambda: net(x)["logits"].argmax(1)
         with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
             for _ in range(5):
-                net(x)["logits"].argmax(1)
+                run()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.iters):
-                pred = net(x)["logits"].argmax(1)
+                pred = run()
             e1.record()
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
         ips = b / ms * 1e3
-        print(json.dumps({"batch": b, "ms_per_batch": ms, "images_per_s": ips,
+        print(json.dumps({"batch": b, "cuda_graph": bool(args.graph), "ms_per_batch": ms, "images_per_s": ips,
                           "fwd_tflops": ips * 35.127 / 1e3, "frac_of_sustained_bf16_peak": ips * 35.127 / 1e3 / peak}),
               flush=True)
         b *= 2
