@@ -128,21 +128,36 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if ((c + 1) * 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < p.N) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < p.N) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
         }
         const float mxs = mx * sl2;
         for (int c = 0; c < nchunks; ++c) {
           uint32_t r[32], pk[16];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if ((c + 1) * 32 <= p.N) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c * 32 + i < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs)) : 0.f;
-            const float p1 = (c * 32 + i + 1 < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs)) : 0.f;
-            sum += p0 + p1;  // fp32 row sum (the saved LSE is the exact log-sum-exp)
-            pk[i >> 1] = pack_bf16(p0, p1);
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs));
+              const float p1 = atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs));
+              sum += p0 + p1;  // fp32 row sum (the saved LSE is the exact log-sum-exp)
+              pk[i >> 1] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = (c * 32 + i < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs)) : 0.f;
+              const float p1 = (c * 32 + i + 1 < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs)) : 0.f;
+              sum += p0 + p1;
+              pk[i >> 1] = pack_bf16(p0, p1);
+            }
           }
           tmem_st_32x16(taddr + c * 16, pk);  // columns this thread has already consumed
         }
@@ -454,26 +469,45 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         mbar_wait(bar_s, it & 1);
         tc_fence_after();
         uint32_t pk[2][16], dk[2][16];
+        const bool rows_live = qt * 128 + quarter * 32 < p.N;  // warp-uniform
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          const int key0 = kb * 128 + hf * 64 + c * 32;
+          if (!rows_live || key0 >= p.N) {  // nothing but padding here: P = dS = 0, no TMEM traffic
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { pk[c][i] = 0u; dk[c][i] = 0u; }
+            continue;
+          }
           uint32_t s[32], d[32];
           tmem_ld_32x32(lane_base + T_S + hf * 64 + c * 32, s);
           tmem_ld_32x32(lane_base + T_DP + hf * 64 + c * 32, d);
           tmem_ld_wait();
-          const int key0 = kb * 128 + hf * 64 + c * 32;
+          if (key0 + 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
+            const float dls = dl * p.scale;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = 0.f, p1 = 0.f, s0 = 0.f, s1 = 0.f;
-            if (key0 + i < p.N) {
-              p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
-              s0 = p0 * (__uint_as_float(d[i]) - dl) * p.scale;
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
+              const float p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
+              const float s0 = p0 * fmaf(__uint_as_float(d[i]), p.scale, -dls);
+              const float s1 = p1 * fmaf(__uint_as_float(d[i + 1]), p.scale, -dls);
+              pk[c][i >> 1] = pack_bf16(p0, p1);
+              dk[c][i >> 1] = pack_bf16(s0, s1);
             }
-            if (key0 + i + 1 < p.N) {
-              p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
-              s1 = p1 * (__uint_as_float(d[i + 1]) - dl) * p.scale;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = 0.f, p1 = 0.f, s0 = 0.f, s1 = 0.f;
+              if (key0 + i < p.N) {
+                p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
+                s0 = p0 * (__uint_as_float(d[i]) - dl) * p.scale;
+              }
+              if (key0 + i + 1 < p.N) {
+                p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
+                s1 = p1 * (__uint_as_float(d[i + 1]) - dl) * p.scale;
+              }
+              pk[c][i >> 1] = pack_bf16(p0, p1);
+              dk[c][i >> 1] = pack_bf16(s0, s1);
             }
-            pk[c][i >> 1] = pack_bf16(p0, p1);
-            dk[c][i >> 1] = pack_bf16(s0, s1);
           }
         }
         if (it > 0) mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 no longer reads sP / sdS
