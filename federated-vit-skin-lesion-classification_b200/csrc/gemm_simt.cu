@@ -22,6 +22,8 @@ struct SimtParams {
   int m, n, k;
   float alpha;
   int tokens_per_img;
+  const float* row_scale;  // RESIDUAL only: per-sample stochastic-depth scale of the branch
+  int rows_per_scale;
 };
 
 template <int EPI>
@@ -85,6 +87,7 @@ gemm_simt_kernel(const SimtParams p) {
       if (EPI == FV_EPI_NONE) {
         C[row * p.ldc + col] = v;
       } else if (EPI == FV_EPI_RESIDUAL) {
+        if (p.row_scale != nullptr) v *= p.row_scale[row / p.rows_per_scale];
         C[row * p.ldc + col] = v + p.aux[row * p.ldaux + col];
       } else if (EPI == FV_EPI_GELU) {
         p.aux[row * p.ldaux + col] = gelu_erf_grad(v);  // kept for the backward instead of v itself
@@ -103,6 +106,11 @@ gemm_simt_kernel(const SimtParams p) {
 }
 
 }  // namespace fv
+
+namespace fv {
+static thread_local const float* g_row_scale_f32 = nullptr;
+static thread_local int g_rows_per_scale_f32 = 0;
+}
 
 extern "C" int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_stride,
                            int64_t a_batch_stride, const float* b, int64_t b_row_stride,
@@ -130,6 +138,8 @@ extern "C" int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_s
   p.m = (int)m; p.n = (int)n; p.k = (int)k;
   p.alpha = alpha;
   p.tokens_per_img = tokens_per_img;
+  p.row_scale = g_row_scale_f32;
+  p.rows_per_scale = g_rows_per_scale_f32;
   dim3 grid(static_cast<unsigned>(ceil_div(n, SM_BN)), static_cast<unsigned>(ceil_div(m, SM_BM)),
             static_cast<unsigned>(batch));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -143,4 +153,17 @@ extern "C" int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_s
   }
   FV_LAUNCH_CHECK();
   return FV_OK;
+}
+
+extern "C" int fv_linear_residual_f32(const float* a, int64_t lda, const float* w, int64_t ldw, const float* bias,
+                                      const float* residual, int64_t ldr, const float* row_scale,
+                                      int64_t rows_per_scale, float* out, int64_t ldo, int64_t m, int64_t n,
+                                      int64_t k, void* stream) {
+  fv::g_row_scale_f32 = row_scale;
+  fv::g_rows_per_scale_f32 = static_cast<int>(rows_per_scale);
+  const int rc = fv_gemm_f32(a, lda, 1, 0, w, ldw, 1, 0, bias, out, ldo, 0, const_cast<float*>(residual), ldr, m, n,
+                             k, 1, 1.0f, FV_EPI_RESIDUAL, 0, stream);
+  fv::g_row_scale_f32 = nullptr;
+  fv::g_rows_per_scale_f32 = 0;
+  return rc;
 }

@@ -46,6 +46,9 @@ struct GemmTcParams {
   void* aux;
   long long ldaux;
   float* colsum;  // wgrad only: += column sums of op(A) (the bias gradient), or nullptr
+  // stochastic depth: RESIDUAL epilogue computes R + row_scale[row / rows_per_scale] * (acc + bias)
+  const float* row_scale;
+  int rows_per_scale;
   // im2col-free patch embedding (FV_EPI_PATCH with im2col == 1): the A operand is the NCHW fp32
   // image itself, fetched by a 5-D TMA map; an M tile is `ph_per_tile` rows of patches of one image
   int im2col;
@@ -233,12 +236,17 @@ __device__ __forceinline__ void stage_flush(uint8_t* stg, void* base, long long 
 // (and `stg2` values for the GELU pre-activation). `mine` holds this row's aux units of the chunk.
 template <int EPI>
 __device__ __forceinline__ void chunk_math(float (&v)[32], const GemmTcParams& p, const float4 (&bv)[8],
-                                           const uint4* mine /*this chunk's aux units or nullptr*/) {
+                                           const uint4* mine /*this chunk's aux units or nullptr*/,
+                                           float rscale) {
   if (EPI != FV_EPI_ACCUM && EPI != FV_EPI_DGELU) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       v[q * 4 + 0] += bv[q].x; v[q * 4 + 1] += bv[q].y; v[q * 4 + 2] += bv[q].z; v[q * 4 + 3] += bv[q].w;
     }
+  }
+  if (EPI == FV_EPI_RESIDUAL && p.row_scale != nullptr) {  // drop-path: scale the branch, not the residual
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= rscale;
   }
   if (EPI == FV_EPI_RESIDUAL || EPI == FV_EPI_PATCH) {  // fp32 aux, 8 units per chunk
 #pragma unroll
@@ -305,6 +313,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
   int nseg = (p.N - n0 + seg_cols - 1) / seg_cols;
   if (nseg > width / seg_cols) nseg = width / seg_cols;
 
+  float rscale = 1.0f;
+  if (EPI == FV_EPI_RESIDUAL && p.row_scale != nullptr) {
+    const long long row = row0 + lane;  // this thread's accumulator row
+    rscale = row < p.M ? __ldg(p.row_scale + row / p.rows_per_scale) : 0.f;
+  }
   uint4 pre[8];
   SegGeom ga{row0, n0, aux_elem};
   if (HAS_AUX_IN) aux_prefetch<EPI>(pre, p, ga, lane);
@@ -344,7 +357,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        chunk_math<EPI>(v, p, bv, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr);
+        chunk_math<EPI>(v, p, bv, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr, rscale);
         if (EPI == FV_EPI_GELU) {
           // Activation AND its derivative from the one cdf/pdf evaluation: out = u*Phi(u) goes to
           // gbuf (stored last), aux = Phi(u) + u*phi(u) replaces the pre-activation as the tensor
@@ -662,6 +675,8 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 
 namespace fv {
 static thread_local float* g_wgrad_colsum = nullptr;
+static thread_local const float* g_row_scale = nullptr;
+static thread_local int g_rows_per_scale = 0;
 }
 
 extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void* b, int b_major,
@@ -713,6 +728,10 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
   p.aux = aux;
   p.ldaux = ldaux;
   p.colsum = g_wgrad_colsum;
+  p.row_scale = g_row_scale;
+  p.rows_per_scale = g_rows_per_scale;
+  FV_CHECK_ARG(p.row_scale == nullptr || (epilogue == FV_EPI_RESIDUAL && p.rows_per_scale > 0),
+               "fv_gemm_bf16: row scaling needs the residual epilogue");
   p.im2col = 0;
   p.gw = p.gh = p.chans = p.ph_per_tile = p.tiles_per_img = 0;
   FV_CHECK_ARG(p.colsum == nullptr || (epilogue == FV_EPI_ACCUM && a_major == FV_MAJOR_MN),
@@ -790,6 +809,8 @@ extern "C" int fv_patch_embed_tf32(const float* img, const float* weight, const 
   p.aux = const_cast<float*>(pos);
   p.ldaux = dim;
   p.colsum = nullptr;
+  p.row_scale = nullptr;
+  p.rows_per_scale = 0;
 
   CUtensorMap ta, tb;
   {  // image viewed as (px, py, pw, ph, b*c); strides in bytes for dims 1..4
@@ -821,4 +842,19 @@ extern "C" int fv_patch_embed_tf32(const float* img, const float* weight, const 
     }
   }
   return launch_gemm_tc<FV_EPI_PATCH>(ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fv_linear_residual_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
+                                       const float* residual, int64_t ldr, const float* row_scale,
+                                       int64_t rows_per_scale, float* out, int64_t ldo, int64_t m, int64_t n,
+                                       int64_t k, void* stream) {
+  // out = residual + row_scale[row / rows_per_scale] * (a w^T + bias): the branch-plus-residual
+  // step of a transformer block with per-sample stochastic depth (row_scale NULL == no drop-path)
+  fv::g_row_scale = row_scale;
+  fv::g_rows_per_scale = static_cast<int>(rows_per_scale);
+  const int rc = fv_gemm_bf16(a, FV_MAJOR_K, lda, w, FV_MAJOR_K, ldw, bias, out, FV_F32, ldo,
+                              const_cast<float*>(residual), ldr, m, n, k, FV_EPI_RESIDUAL, 1, 0, stream);
+  fv::g_row_scale = nullptr;
+  fv::g_rows_per_scale = 0;
+  return rc;
 }

@@ -90,7 +90,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_lp,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
-                     int cols) {
+                     int cols, const float* __restrict__ lp_scale, int rows_per_scale) {
   pdl_wait();
   extern __shared__ float red[];       // [2][LNB_ROWS][cols] for the final dgamma / dbeta reduction
   __shared__ float2 stat[LNB_ROWS][2];  // per warp pair: partial (s1, s2) of each warp
@@ -153,6 +153,9 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
     s1 = (a.x + b2.x) * inv_cols;
     s2 = (a.y + b2.y) * inv_cols;
     if (live) {
+      // stochastic depth: the bf16 copy feeds the *branch* GEMMs of the preceding sub-layer, whose
+      // output was scaled per sample in the forward — scale its gradient the same way
+      const float lps = lp_scale != nullptr ? __ldg(lp_scale + row / rows_per_scale) : 1.0f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = t64 + 64 * i;
@@ -169,8 +172,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
           reinterpret_cast<float4*>(dx + row * cols)[c] = o;
           if (dx_lp != nullptr) {
             uint2 pk;
-            pk.x = pack_bf16(o.x, o.y);
-            pk.y = pack_bf16(o.z, o.w);
+            pk.x = pack_bf16(o.x * lps, o.y * lps);
+            pk.y = pack_bf16(o.z * lps, o.w * lps);
             reinterpret_cast<uint2*>(dx_lp + row * cols)[c] = pk;
           }
         }
@@ -237,7 +240,7 @@ extern "C" int fv_layernorm_fwd(const float* x, const float* gamma, const float*
 extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
                                 const float* mean, const float* rstd, const float* dres, float* dx,
                                 void* dx_lp, float* dgamma, float* dbeta, int64_t rows, int64_t cols,
-                                void* stream) {
+                                const float* lp_row_scale, int64_t rows_per_scale, void* stream) {
   using namespace fv;
   FV_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta,
                "fv_layernorm_bwd: null pointer");
@@ -245,6 +248,8 @@ extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, co
                "fv_layernorm_bwd: cols=%lld must be a multiple of 4 and <= %d", (long long)cols,
                LN_MAX_VEC * 128);
   FV_CHECK_ARG(dy_dtype == FV_F32 || dy_dtype == FV_BF16, "fv_layernorm_bwd: bad dy_dtype");
+  FV_CHECK_ARG(lp_row_scale == nullptr || (rows_per_scale > 0 && dx_lp != nullptr),
+               "fv_layernorm_bwd: lp_row_scale needs dx_lp and rows_per_scale > 0");
   if (rows == 0) return FV_OK;
   int64_t want = ceil_div(rows, LNB_ROWS);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 3;
@@ -254,7 +259,7 @@ extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, co
   __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(dx_lp);
 #define FV_LN_BWD(NV, BF)                                                                        \
   FV_CHECK_CUDA(fv::launch_pdl(layernorm_bwd_kernel<NV, BF>, dim3(grid), dim3(LNB_THREADS), smem, st, dy, x, gamma, mean, rstd, dres, dx, \
-                                                                lp, dgamma, dbeta, rows, (int)cols))
+                                                                lp, dgamma, dbeta, rows, (int)cols, lp_row_scale, (int)rows_per_scale))
 #define FV_LN_BWD_NV(NV)                          \
   do {                                            \
     if (dy_dtype == FV_BF16) FV_LN_BWD(NV, true); \

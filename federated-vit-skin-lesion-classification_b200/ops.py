@@ -136,6 +136,35 @@ def gemm_gelu(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor, pre: Te
     _gemm_impl(a, b, bias, out, pre, MAJOR_K, MAJOR_K, EPI["gelu"], 1, 0)
 
 
+@torch.library.custom_op("fedvit::linear_residual", mutates_args=("out",))
+def linear_residual(a: Tensor, w: Tensor, bias: Optional[Tensor], residual: Tensor, row_scale: Optional[Tensor],
+                    rows_per_scale: int, out: Tensor) -> None:
+    """out = residual + row_scale[row // rows_per_scale] * (a @ w^T + bias) — a block's branch +
+    residual with per-sample stochastic depth (``row_scale=None``: plain residual add)."""
+    _need_cuda(a, w, bias, residual, row_scale, out)
+    m, k = a.shape
+    n = w.shape[0]
+    if w.shape[1] != k or tuple(out.shape) != (m, n) or tuple(residual.shape) != (m, n):
+        raise FedVitError("linear_residual: shape mismatch")
+    if row_scale is not None and (row_scale.dtype != torch.float32 or rows_per_scale <= 0
+                                  or row_scale.numel() * rows_per_scale < m):
+        raise FedVitError("linear_residual: row_scale must be fp32 with one entry per rows_per_scale rows")
+    name = "fv_linear_residual_bf16" if a.dtype == torch.bfloat16 else "fv_linear_residual_f32"
+    if a.dtype != w.dtype or a.dtype not in (torch.bfloat16, torch.float32):
+        raise FedVitError("linear_residual: operands must both be bf16 or both fp32")
+    trace = GEMM_TRACE if a.dtype == torch.bfloat16 else None
+    if trace is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    LIB.call(name, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), residual.data_ptr(),
+             residual.stride(0), _ptr(row_scale), rows_per_scale, out.data_ptr(), out.stride(0), m, n, k,
+             _stream(a))
+    if trace is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        trace.append((e0, e1, 2.0 * m * n * k))
+
+
 @torch.library.custom_op("fedvit::wgrad", mutates_args=("dw", "dbias"))
 def wgrad(dy: Tensor, x: Tensor, dw: Tensor, dbias: Optional[Tensor], split_k: int) -> None:
     """dw[out,in] += dy^T @ x and dbias[out] += dy.sum(0), bf16 operands, one tensor-core kernel."""
@@ -204,21 +233,24 @@ def _(x, gamma, beta, eps, out_bf16):
 
 @torch.library.custom_op("fedvit::layernorm_bwd", mutates_args=("dgamma", "dbeta"))
 def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor,
-                  dres: Optional[Tensor], dgamma: Tensor, dbeta: Tensor, want_lp: bool) -> Tuple[Tensor, Tensor]:
-    """dx = dres + LN'(dy); dgamma/dbeta are accumulated in place. Returns (dx fp32, dx bf16|empty)."""
-    _need_cuda(dy, x, gamma, mean, rstd, dres, dgamma, dbeta)
+                  dres: Optional[Tensor], dgamma: Tensor, dbeta: Tensor, want_lp: bool,
+                  lp_scale: Optional[Tensor] = None, rows_per_scale: int = 0) -> Tuple[Tensor, Tensor]:
+    """dx = dres + LN'(dy); dgamma/dbeta are accumulated in place. Returns (dx fp32, dx bf16|empty).
+    ``lp_scale`` (fp32, one value per ``rows_per_scale`` rows) multiplies the bf16 copy only
+    (stochastic depth of the sub-layer that consumes it)."""
+    _need_cuda(dy, x, gamma, mean, rstd, dres, dgamma, dbeta, lp_scale)
     rows, cols = x.shape
     dx = torch.empty_like(x)
     dx_lp = torch.empty((rows, cols) if want_lp else (0,), device=x.device, dtype=torch.bfloat16)
     LIB.call("fv_layernorm_bwd", dy.data_ptr(), _dt(dy), x.data_ptr(), gamma.data_ptr(),
              mean.data_ptr(), rstd.data_ptr(), _ptr(dres), dx.data_ptr(),
              dx_lp.data_ptr() if want_lp else None, dgamma.data_ptr(), dbeta.data_ptr(), rows, cols,
-             _stream(x))
+             _ptr(lp_scale) if want_lp else None, rows_per_scale, _stream(x))
     return dx, dx_lp
 
 
 @layernorm_bwd.register_fake
-def _(dy, x, gamma, mean, rstd, dres, dgamma, dbeta, want_lp):
+def _(dy, x, gamma, mean, rstd, dres, dgamma, dbeta, want_lp, lp_scale=None, rows_per_scale=0):
     return torch.empty_like(x), x.new_empty(x.shape if want_lp else (0,), dtype=torch.bfloat16)
 
 

@@ -316,8 +316,14 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         images = n_total * local_epochs  # all ranks together (drop_last: whole batches only)
         images = sum((s // int(t.get("batch_size", 16))) * int(t.get("batch_size", 16)) for s in sizes) * local_epochs
+        # sample-weighted mean of the clients' epoch losses over ALL ranks (logging only)
+        lw = torch.tensor([sum(l * sizes[c] for l, c in zip(losses[local_epochs - 1::local_epochs], mine)),
+                           float(sum(sizes[c] for c in mine))], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(lw)
         rec = {"round": rnd, "round_ms": float(ms[0]), "aggregate_ms": float(ms[1]),
-               "images_per_s": images / (float(ms[0]) / 1e3), "mean_client_loss": float(np.mean(losses)) if losses else None}
+               "images_per_s": images / (float(ms[0]) / 1e3),
+               "mean_client_loss": float(lw[0] / lw[1]) if float(lw[1]) > 0 else None}
         if val_loader is not None:
             if ema is not None:
                 ema.apply_shadow()

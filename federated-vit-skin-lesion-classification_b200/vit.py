@@ -173,6 +173,17 @@ class VisionTransformer(nn.Module):
                 nn.init.zeros_(m.bias)
 
     # ------------------------------------------------------------------------------------------
+    def _drop_path_scale(self, rate: float, batch: int, device) -> Optional[Tensor]:
+        """Per-sample stochastic-depth factor mask / keep_prob (timm DropPath, scale_by_keep=True),
+        or None when the branch is always kept (eval mode or rate 0)."""
+        if not self.training or rate <= 0.0:
+            return None
+        keep = 1.0 - rate
+        mask = torch.empty(batch, device=device, dtype=torch.float32).bernoulli_(keep)
+        if keep > 0.0:
+            mask.div_(keep)
+        return mask
+
     def _bb_params(self) -> List[nn.Parameter]:
         return list(self.parameters())
 
@@ -199,11 +210,6 @@ class VisionTransformer(nn.Module):
             raise ValueError(f"input {tuple(x.shape[-2:])} != model image size {pe.img_size}")
         if x.shape[1] != pe.proj.weight.shape[1]:
             raise ValueError(f"input has {x.shape[1]} channels, patch_embed.proj expects {pe.proj.weight.shape[1]}")
-        if self.training and any(b.drop_path_rate > 0 for b in self.blocks):
-            raise NotImplementedError(
-                "stochastic depth (drop_path_rate > 0) is not on the B200 path yet; set "
-                "model.drop_path_rate: 0 (the parity / benchmark configurations do, SURVEY.md §8d)"
-            )
         lp = torch.is_autocast_enabled("cuda")
         if lp:
             a = getattr(self.cls_token, "_fv_arena", None)
@@ -301,17 +307,19 @@ class VisionTransformer(nn.Module):
             qkv = torch.empty((M, 3 * D), device=dev, dtype=act)
             ops.gemm(h, self._w(at.qkv.weight, lp), at.qkv.bias.detach(), qkv, None, _K, _K, _E["none"], 1, 0)
             o, aux = self._attention_fwd(qkv, B, N, lp)
+            s1 = self._drop_path_scale(blk.drop_path_rate, B, dev)
+            s2 = self._drop_path_scale(blk.drop_path_rate, B, dev)
             x1 = torch.empty((M, D), device=dev, dtype=torch.float32)
-            ops.gemm(o, self._w(at.proj.weight, lp), at.proj.bias.detach(), x1, x, _K, _K, _E["residual"], 1, 0)
+            ops.linear_residual(o, self._w(at.proj.weight, lp), at.proj.bias.detach(), x, s1, N, x1)
             h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2.weight.detach(), n2.bias.detach(), n2.eps, lp)
             hid = mlp.fc1.weight.shape[0]
             u = torch.empty((M, hid), device=dev, dtype=act)
             a = torch.empty((M, hid), device=dev, dtype=act)
             ops.gemm_gelu(h2, self._w(mlp.fc1.weight, lp), mlp.fc1.bias.detach(), a, u)
             x2 = torch.empty((M, D), device=dev, dtype=torch.float32)
-            ops.gemm(a, self._w(mlp.fc2.weight, lp), mlp.fc2.bias.detach(), x2, x1, _K, _K, _E["residual"], 1, 0)
+            ops.linear_residual(a, self._w(mlp.fc2.weight, lp), mlp.fc2.bias.detach(), x1, s2, N, x2)
             if save:
-                st.blocks.append((x, h, mean1, rstd1, qkv, o, aux, x1, h2, mean2, rstd2, u, a))
+                st.blocks.append((x, h, mean1, rstd1, qkv, o, aux, x1, h2, mean2, rstd2, u, a, s1, s2))
             x = x2
 
         cls_rows = x.view(B, N, D)[:, 0].contiguous()
@@ -349,14 +357,22 @@ class VisionTransformer(nn.Module):
         return dx
 
     def _ln_bwd(self, dy: Tensor, x: Tensor, ln: nn.LayerNorm, mean: Tensor, rstd: Tensor,
-                dres: Optional[Tensor], lp: bool) -> Tuple[Tensor, Tensor]:
+                dres: Optional[Tensor], lp: bool, branch_scale: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """Returns (dx fp32, the gradient the preceding sub-layer's branch GEMMs consume): dx in the
+        GEMM operand type, times that branch's stochastic-depth factor when it has one."""
         if ln.weight.requires_grad:
             dg, db = _grad_buffer(ln.weight), _grad_buffer(ln.bias)
         else:
             dg = torch.zeros_like(ln.weight)
             db = torch.zeros_like(ln.bias)
-        dx, dx_lp = ops.layernorm_bwd(dy, x, ln.weight.detach(), mean, rstd, dres, dg, db, lp)
-        return dx, (dx_lp if lp else dx)
+        rows_per = self.num_tokens if branch_scale is not None else 0
+        dx, dx_lp = ops.layernorm_bwd(dy, x, ln.weight.detach(), mean, rstd, dres, dg, db, lp,
+                                      branch_scale if lp else None, rows_per)
+        if lp:
+            return dx, dx_lp
+        if branch_scale is not None:  # fp32 parity path: explicit scaled copy
+            return dx, (dx.view(-1, self.num_tokens, dx.shape[1]) * branch_scale.view(-1, 1, 1)).view_as(dx)
+        return dx, dx
 
     def _backward_impl(self, st: _Saved, dfeats: Tensor) -> None:
         lp, B, N = st.lp, st.B, st.N
@@ -366,19 +382,28 @@ class VisionTransformer(nn.Module):
         dcls, _ = self._ln_bwd(dfeats.float().contiguous(), st.cls_rows, self.norm, st.meanf, st.rstdf, None, False)
         dx = torch.zeros((M, D), device=dev, dtype=torch.float32)
         dx.view(B, N, D)[:, 0] = dcls
-        dy = _to_bf16(dx) if lp else dx
+        last_s2 = st.blocks[-1][-1]
+        if last_s2 is not None:  # the last block's MLP branch carried a stochastic-depth factor
+            dyf = dx.clone()
+            dyf.view(B, N, D)[:, 0] *= last_s2.view(B, 1)
+            dy = _to_bf16(dyf) if lp else dyf
+        else:
+            dy = _to_bf16(dx) if lp else dx
 
-        for blk, saved in zip(reversed(self.blocks), reversed(st.blocks)):
-            (x, h, mean1, rstd1, qkv, o, aux, x1, h2, mean2, rstd2, u, a) = saved
-            # MLP branch: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
+        nblk = len(st.blocks)
+        for i in range(nblk - 1, -1, -1):
+            blk = self.blocks[i]
+            (x, h, mean1, rstd1, qkv, o, aux, x1, h2, mean2, rstd2, u, a, s1, s2) = st.blocks[i]
+            prev_s2 = st.blocks[i - 1][-1] if i > 0 else None
+            # MLP branch: x2 = x1 + s2 * fc2(gelu(fc1(LN2(x1))))   (dy already carries s2)
             du = self._linear_bwd(dy, a, blk.mlp.fc2, lp, True, dgelu_aux=u)
             dh2 = self._linear_bwd(du, h2, blk.mlp.fc1, lp, True)
-            dx1, dy1 = self._ln_bwd(dh2, x1, blk.norm2, mean2, rstd2, dx, lp)
-            # attention branch: x1 = x + proj(attn(qkv(LN1(x))))
+            dx1, dy1 = self._ln_bwd(dh2, x1, blk.norm2, mean2, rstd2, dx, lp, branch_scale=s1)
+            # attention branch: x1 = x + s1 * proj(attn(qkv(LN1(x))))
             do = self._linear_bwd(dy1, o, blk.attn.proj, lp, True)
             dqkv = self._attention_bwd(qkv, o, do, aux, B, N, lp)
             dh = self._linear_bwd(dqkv, h, blk.attn.qkv, lp, True)
-            dx, dy = self._ln_bwd(dh, x, blk.norm1, mean1, rstd1, dx1, lp)
+            dx, dy = self._ln_bwd(dh, x, blk.norm1, mean1, rstd1, dx1, lp, branch_scale=prev_s2)
 
         # embedding: x0[b] = cat(cls, patches[b] W^T + b) + pos
         if self.pos_embed.requires_grad:

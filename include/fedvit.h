@@ -89,6 +89,19 @@ int fv_wgrad_bf16(const void* dy, int64_t lddy, const void* x, int64_t ldx, floa
                   float* dbias, int64_t tokens, int64_t out_features, int64_t in_features,
                   int split_k, void* stream);
 
+/* Branch + residual of a transformer block with per-sample stochastic depth (timm DropPath):
+ *   out[r,:] = residual[r,:] + row_scale[r / rows_per_scale] * (a[r,:] w^T + bias)
+ * row_scale (fp32, one value per image: keep_mask / keep_prob) may be NULL (plain residual).
+ * bf16: a [m,k], w [n,k] bf16; f32: fp32 operands. residual / out fp32.                          */
+int fv_linear_residual_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
+                            const float* residual, int64_t ldr, const float* row_scale,
+                            int64_t rows_per_scale, float* out, int64_t ldo, int64_t m, int64_t n,
+                            int64_t k, void* stream);
+int fv_linear_residual_f32(const float* a, int64_t lda, const float* w, int64_t ldw, const float* bias,
+                           const float* residual, int64_t ldr, const float* row_scale,
+                           int64_t rows_per_scale, float* out, int64_t ldo, int64_t m, int64_t n,
+                           int64_t k, void* stream);
+
 int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_stride, int64_t a_batch_stride,
                 const float* b, int64_t b_row_stride, int64_t b_col_stride, int64_t b_batch_stride,
                 const float* bias,
@@ -103,6 +116,8 @@ int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_stride, int6
  *   x fp32 [rows, cols]; y is y_dtype; mean/rstd fp32 [rows] are saved for the backward.
  * Backward: dx = dres + LN'(dy) in fp32, optional bf16 copy of dx (dx_lp) for the next GEMM;
  *   dgamma/dbeta are ACCUMULATED (+=) into fp32 [cols] (zero them first for a fresh gradient).
+ *   lp_row_scale (optional, fp32, one value per rows_per_scale rows): the bf16 copy is written as
+ *   dx * scale — the per-sample stochastic-depth factor of the sub-layer that consumes it.
  * ---------------------------------------------------------------------------------------- */
 int fv_layernorm_fwd(const float* x, const float* gamma, const float* beta,
                      void* y, int y_dtype, float* mean, float* rstd,
@@ -110,7 +125,8 @@ int fv_layernorm_fwd(const float* x, const float* gamma, const float* beta,
 int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
                      const float* mean, const float* rstd, const float* dres,
                      float* dx, void* dx_lp, float* dgamma, float* dbeta,
-                     int64_t rows, int64_t cols, void* stream);
+                     int64_t rows, int64_t cols,
+                     const float* lp_row_scale, int64_t rows_per_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-head self-attention core, softmax(Q K^T * scale) V, no mask, no dropout.

@@ -61,6 +61,16 @@ def test_gemm_bf16_epilogues():
     out = torch.empty(m, n, device=DEV)
     ops.gemm(a, b, bias, out, res, 0, 0, ops.EPI["residual"], 1, 0)
     assert rel_err(out, ref + bias + res) < 1e-5
+    # + residual with a per-sample stochastic-depth factor on the branch
+    groups = 7
+    scale = torch.rand((m + groups - 1) // groups, device=DEV, generator=g) * 2
+    out = torch.empty(m, n, device=DEV)
+    ops.linear_residual(a, b, bias, res, scale, groups, out)
+    rows = torch.arange(m, device=DEV) // groups
+    assert rel_err(out, (ref + bias) * scale[rows, None] + res) < 1e-5
+    out32 = torch.empty(m, n, device=DEV)
+    ops.linear_residual(a.float(), b.float(), bias, res, scale, groups, out32)
+    assert rel_err(out32, (ref + bias) * scale[rows, None] + res) < 1e-5
     # GELU + its derivative (kept for the backward), fp32 and bf16 stores
     pre = (ref + bias).double().requires_grad_(True)
     act_ref = torch.nn.functional.gelu(pre)
@@ -141,6 +151,10 @@ def test_layernorm_fwd_bwd(cols):
     assert rel_err(dg, gr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
     ops.layernorm_bwd(dy, x, gam, mean, rstd, None, dg, db, False)  # accumulates
     assert rel_err(dg, 2 * gr.grad) < 1e-5
+    sc = torch.rand((rows + 12) // 13, device=DEV, generator=g) + 0.5
+    dxs, dxs_lp = ops.layernorm_bwd(dy, x, gam, mean, rstd, dres, torch.zeros_like(dg), torch.zeros_like(db), True, sc, 13)
+    assert torch.equal(dxs, dx)
+    assert rel_err(dxs_lp, dx * sc[torch.arange(rows, device=DEV) // 13, None]) < 4e-3
     ybf, _, _ = ops.layernorm_fwd(x, gam, bet, 1e-6, True)
     assert rel_err(ybf, yr) < 4e-3
     dxb, _ = ops.layernorm_bwd(dy.bfloat16(), x, gam, mean, rstd, None, torch.zeros_like(dg), torch.zeros_like(db), False)

@@ -378,3 +378,108 @@ def test_graphed_eval_forward_matches_eager():
     assert torch.equal(fwd(x2), eager2)
     with pytest.raises(ValueError):
         fwd(x2[:2])
+
+
+def test_config1_vit_tiny_fedavg_round_fp32_vs_oracle():
+    """BASELINE configs[0] end to end: ViT-Tiny/16 224, 2 FedAvg clients, 1 local epoch, batch 16,
+    64 samples per client, fp32 — the whole round on the GPU vs the CPU oracle doing the same
+    (local epochs with torch AdamW over the LLRD groups, then the sequential fp32 FedAvg)."""
+    cfg = {
+        "seed": 42,
+        "model": {"backbone": "vit_tiny_patch16_224", "num_classes": 7, "image_size": 224, "pretrained": False,
+                  "drop_path_rate": 0.0, "metadata": {"enabled": False}, "classifier": {"hidden_dim": 512, "dropout": 0.0}},
+        "data": {"use_segmentation_mask": False},
+        "training": {"use_amp": False, "grad_clip": 1.0, "gradient_accumulation_steps": 1, "batch_size": 16,
+                     "optimizer": {"lr": 2e-5, "weight_decay": 1e-5}, "llrd": {"enabled": True, "decay_rate": 0.75}},
+        "augmentation": {"mixup": {"alpha": 0.0}, "cutmix": {"prob": 0.0}},
+        "loss": {"asymmetric": {"gamma_neg": 4, "gamma_pos": 1, "clip": 0.05}},
+        "federated": {"num_clients": 2, "rounds": 1, "local_epochs": 1, "samples_per_client": 64},
+    }
+    out = train.run_federated(cfg, device=DEV)
+    ours = out["model"].eval()
+    utils.seed_everything(42)
+    init = model.build_model(cfg).state_dict()
+    finals = []
+    for c in range(2):
+        ora = isic.model_from_config(cfg)
+        ora.load_state_dict(init)
+        loader = data.SyntheticClientLoader(c, 64, 16, 224, num_classes=7, pin=False)
+        oopt = torch.optim.AdamW(isic.llrd_groups(ora, 2e-5, 0.75, 1e-5), weight_decay=1e-5)
+        loss = step.local_epoch(ora, list(loader), asl.loss_from_config(cfg), oopt, grad_clip=1.0)
+        finals.append({k: v.clone() for k, v in ora.state_dict().items()})
+    want = ofed.fedavg_state_dicts(finals, [64, 64])
+    glob = isic.model_from_config(cfg).eval()
+    glob.load_state_dict(want)
+    probe = torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        a, b = ours(probe.to(DEV))["logits"], glob(probe)["logits"]
+    assert rel_err(a, b) < 2e-2  # Adam-noise amplified (POST_ADAM_TOL note); first-step parity is 1e-6
+    assert torch.equal(a.argmax(1).cpu(), b.argmax(1))
+    assert out["rounds"][0]["mean_client_loss"] == pytest.approx(loss, rel=0.2)
+
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_stochastic_depth_matches_oracle_with_shared_masks(amp):
+    """drop_path_rate > 0 (the reference's default is 0.4, config.yaml:32): per-sample keep masks,
+    branch scaled by 1/keep_prob in the forward epilogue and in the backward operand. Both sides are
+    fed the same masks; fp32 gate 1e-4, bf16 gate 2e-2."""
+    from oracle.timm.models import vision_transformer as ovt
+
+    cfg = micro_config()
+    cfg["model"]["backbone"] = "vit_tiny_patch16_224"
+    cfg["model"]["image_size"] = 224
+    cfg["model"]["drop_path_rate"] = 0.4
+    torch.manual_seed(11)
+    ora = isic.model_from_config(cfg).train()
+    ours = model.build_model(cfg)
+    ours.load_state_dict(ora.state_dict())
+    ours = ours.to(DEV).train()
+    B = 6
+    g = torch.Generator().manual_seed(21)
+    x, y = torch.randn(B, 3, 224, 224, generator=g), torch.randint(0, 7, (B,), generator=g)
+    rates = [b.drop_path_rate for b in ours.backbone.blocks]
+    assert rates[0] == 0.0 and rates[-1] == pytest.approx(0.4)
+    masks = {}
+    for i, r in enumerate(rates):
+        if r > 0:
+            masks[i] = [torch.empty(B).bernoulli_(1 - r, generator=g) / (1 - r) for _ in range(2)]
+
+    # oracle: replace every DropPath by a fixed-mask multiply
+    for i, blk in enumerate(ora.backbone.blocks):
+        if i in masks:
+            for j, name in enumerate(("drop_path1", "drop_path2")):
+                m = masks[i][j]
+
+                class Fixed(torch.nn.Module):
+                    def __init__(self, m):
+                        super().__init__()
+                        self.m = m
+
+                    def forward(self, t):
+                        return t * self.m.view(-1, 1, 1)
+
+                setattr(blk, name, Fixed(m))
+    # ours: the backbone asks for its factors block by block, branch by branch
+    queue = []
+    for i in range(len(rates)):
+        queue += [masks[i][0], masks[i][1]] if i in masks else [None, None]
+    it = iter(queue)
+    ours.backbone._drop_path_scale = lambda rate, batch, device: (lambda m: None if m is None else m.to(device))(next(it))
+
+    want_logits, want_loss, want_grads = _oracle_grads(ora, x, y)
+    tol = 2e-2 if amp else 1e-4
+    if amp:
+        FlatArena(ours)
+    with torch.amp.autocast("cuda", enabled=amp, dtype=torch.bfloat16):
+        logits = ours(x.to(DEV))["logits"]
+        loss = losses.AsymmetricFocalLoss()(logits, y.to(DEV))
+    loss.backward()
+    assert rel_err(logits, want_logits) < tol
+    worst, who = _grad_errs(ours, want_grads)
+    assert worst < tol, (who, worst)
+    # eval mode: no masks are drawn, the forward is deterministic
+    ours.eval()
+    del ours.backbone._drop_path_scale
+    with torch.no_grad():
+        a, b = ours(x.to(DEV))["logits"], ours(x.to(DEV))["logits"]
+    assert torch.equal(a, b)
