@@ -78,7 +78,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 // per CTA pass, grid-stride over rows. Splitting the row keeps the per-thread state (x-hat, g*dy
 // and the running dgamma / dbeta slices) near 80 registers — three CTAs per SM instead of the one
 // or two a warp-per-row layout gets — which is what an HBM-bound kernel needs. The two row
-// statistics cross the warp pair through shared memory; dgamma / dbeta are reduced over the CTA's
+// statistics cross the warp pair through shared memory (pair-local named barriers, no CTA-wide
+// sync in the row loop); dgamma / dbeta are reduced over the CTA's
 // four row slots in shared memory and leave with one atomicAdd per column per CTA.
 constexpr int LNB_THREADS = 256;
 constexpr int LNB_ROWS = 4;  // rows in flight per CTA (one per warp pair)
@@ -109,10 +110,10 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   const float inv_cols = 1.0f / cols;
   const long long stride = static_cast<long long>(gridDim.x) * LNB_ROWS;
   const long long first = static_cast<long long>(blockIdx.x) * LNB_ROWS;
-  // every warp runs the same number of passes (the CTA-wide barriers below need that)
-  for (long long base = first; base < rows; base += stride) {
-    const long long row = base + slot;
-    const bool live = row < rows;
+  // each warp pair walks its own rows and only ever synchronises with its partner (named barrier
+  // slot+1, 64 threads): no CTA-wide barrier inside the loop, so pairs overlap each other's latency
+  for (long long row = first + slot; row < rows; row += stride) {
+    const bool live = true;
     float4 xh[NV], gy[NV];
     float s1 = 0.f, s2 = 0.f;
     float mu = 0.f, rs = 0.f;
@@ -148,7 +149,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane == 0) stat[slot][warp & 1] = make_float2(s1, s2);
-    __syncthreads();
+    asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
     const float2 a = stat[slot][0], b2 = stat[slot][1];
     s1 = (a.x + b2.x) * inv_cols;
     s2 = (a.y + b2.y) * inv_cols;
@@ -179,7 +180,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
         }
       }
     }
-    __syncthreads();  // stat[] is rewritten by the next pass
+    asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");  // stat[] is rewritten by the next pass
   }
   // CTA reduction of the four row slots' dgamma / dbeta slices
   float* red_g = red;
