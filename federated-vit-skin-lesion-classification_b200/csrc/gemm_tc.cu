@@ -558,8 +558,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // dY tiles (A operand, MN-major: [64 token rows x 128 output columns] per stage, two
         // 128B-swizzled boxes), the otherwise idle epilogue warps add up their columns. Thread ->
         // (column pair = tid % 64, 16-token group = tid / 64): 16 conflict-free 32-bit smem reads
-        // per stage. Only the n_blk == 0 CTA of each row block contributes; every CTA follows the
-        // same full/empty protocol.
+        // per stage. The CTAs that share a row block (one per n_blk, same dY tiles) split its
+        // k-slices round-robin, so the extra shared-memory traffic is spread evenly instead of
+        // slowing one CTA in num_n_blocks; every CTA follows the same full/empty protocol.
         const int et = threadIdx.x - 128;
         const int cp = et & 63, rg = et >> 6;  // column pair (2 bf16 = one 32-bit word), 16-row group
         const int kb0 = split * p.kb_per_split;
@@ -568,7 +569,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           if (lane == 0) mbar_wait(&full_bar[cs_stage], cs_phase);  // one poller per warp
           __syncwarp();
-          if (n_blk == 0) {
+          if (kb % p.num_n_blocks == n_blk) {  // this CTA's share of the row block's k-slices
             const uint8_t* sa = smem + cs_stage * STAGE_BYTES + (cp >> 5) * (64 * BK * 2) + (cp & 3) * 4;
             const int unit = (cp & 31) >> 2;
 #pragma unroll
@@ -583,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (lane == 0) mbar_arrive(&empty_bar[cs_stage]);
           if (++cs_stage == STAGES) { cs_stage = 0; cs_phase ^= 1; }
         }
-        if (n_blk == 0) {
+        {
           float* red = reinterpret_cast<float*>(tmem_slot + 8);  // 128 floats after the barriers
           if (et < 128) red[et] = 0.f;
           asm volatile("bar.sync 1, 256;" ::: "memory");
