@@ -236,7 +236,7 @@ def run_gpu_arm(args) -> None:
     for i in range(args.warmup):
         step(i)
     barrier()
-    ops.GEMM_TRACE = []
+    ops.GEMM_TRACE = None if os.environ.get("FEDVIT_BENCH_NOTRACE") else []  # A/B switch: cost of the per-GEMM events
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -248,7 +248,7 @@ def run_gpu_arm(args) -> None:
         barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - n0
-    trace, ops.GEMM_TRACE = ops.GEMM_TRACE, None
+    trace, ops.GEMM_TRACE = ops.GEMM_TRACE or [], None
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in trace)
     gemm_flops = sum(f for _, _, f in trace)
     final_loss = float(loss.detach())

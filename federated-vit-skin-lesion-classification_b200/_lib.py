@@ -83,7 +83,17 @@ class _Lib:
     def call(self, name: str, *args):
         if self._dll is None:
             self.load()
-        rc = self._fns[name](*args)
+        trace = TRACE
+        if trace is not None:  # tools/step_breakdown.py: live per-launch device times
+            import torch
+
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = self._fns[name](*args)
+            e1.record()
+            trace.append((name, args, e0, e1))
+        else:
+            rc = self._fns[name](*args)
         if rc != 0:
             msg = self._fns["fv_last_error"]()
             raise FedVitError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
@@ -93,6 +103,10 @@ class _Lib:
             self.load()
         return self._fns[name]
 
+
+# when set to a list, every C-ABI call is bracketed by CUDA events on the current stream and
+# (name, args, start, end) is appended (measurement tooling only)
+TRACE = None
 
 LIB = _Lib()
 

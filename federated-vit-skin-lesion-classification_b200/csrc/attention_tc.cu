@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                    const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space
+  // known to the compiler: LDS / STS instead of generic LD / ST for every staging access
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                         // 2 x 16 KiB (both query tiles); reused as output staging
   uint8_t* sK = sQ + 2 * ATC_Q * 128;         // 32 KiB
   uint8_t* sV = sK + ATC_KV_MAX * 128;        // 32 KiB
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const __grid_constant__ CUtensorMap tmap_o, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space
+  // known to the compiler: LDS / STS instead of generic LD / ST for every staging access
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                  // 2 tiles
   uint8_t* sdO = sQ + 2 * ATB_TILE;    // 2 tiles
   uint8_t* sO = sdO + 2 * ATB_TILE;    // 2 tiles (forward output, only for delta = rowsum(dO * O))

@@ -17,6 +17,8 @@
 //                              pre-activation inputs take the same path in reverse and are
 //                              prefetched one segment ahead so their latency hides behind the MMAs.
 // The epilogue of tile i overlaps the main loop of tile i+1 through the two TMEM stages.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fv {
@@ -54,6 +56,9 @@ struct GemmTcParams {
   int im2col;
   int gw, gh, chans;       // patch grid and input channels
   int ph_per_tile, tiles_per_img;
+  int tma_out;  // outputs leave through TMA tensor stores (everything but the PATCH row remap)
+  int direct;  // epilogue without smem staging (needs 32-byte aligned rows of c / aux)
+  int dbg;  // FEDVIT_GEMM_DBG (measurement only): 1 = epilogue without global stores, 2 = no epilogue work
 };
 
 // PATCH epilogue row mapping: local row r of M tile m_blk -> (valid?, global output row, pos row)
@@ -78,11 +83,14 @@ __device__ __forceinline__ bool patch_row(const GemmTcParams& p, long long row0,
   return true;
 }
 
-// exact-GELU pieces in ~16 issue slots: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), sharing
-// the one exponential exp(-x^2/2) between the cdf and the pdf; the two transcendental steps are
-// single MUFU instructions (rcp.approx.ftz / ex2.approx.ftz — no range-fixup code around them).
-// erff()/__expf()/__fdividef() cost 3 MUFU + ~25 FP32 ops per element and made the fc1 / fc2-dgrad
-// epilogues XU-bound (ncu: xu pipe 55 %, tensor pipe 19 %), see profiles/.
+// exact-GELU pieces on packed fp32 pairs. Phi(x) by Abramowitz-Stegun 26.2.17 (|err| <= 7.5e-8):
+//   1 - Phi(|x|) = phi(|x|) * (b1 t + ... + b5 t^5),  t = 1 / (1 + 0.2316419 |x|),
+// sharing the one exponential phi(x) = exp(-x^2/2)/sqrt(2 pi) between the cdf and the derivative.
+// The two transcendental steps are single MUFU instructions (rcp.approx.ftz / ex2.approx.ftz, no
+// range-fixup code); everything else is FFMA2 / FMUL2 / FADD2, one FMA-pipe issue per TWO
+// elements. History (profiles/): erff()/__expf() 3 MUFU + ~25 FP32 ops per element made the fc1 /
+// fc2-dgrad epilogues XU-bound; the scalar A&S form (17 FMA-pipe ops per element) left them
+// FMA-pipe-bound at K = 768; the packed form needs ~7 FMA-pipe issues per element.
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -93,27 +101,28 @@ __device__ __forceinline__ float rcp_ftz(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_ftz(fmaf(0.3275911f, z, 1.0f));
-  const float e = ex2_ftz(x * x * -0.72134752044448170368f);  // exp(-x^2/2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float half_erf = fmaf(poly * t, -0.5f * e, 0.5f);  // erf(|x|/sqrt2) / 2
-  cdf = 0.5f + copysignf(half_erf, x);
-  pdf = 0.39894228040143267794f * e;
+__device__ __forceinline__ uint32_t copysign_bits(float mag, float sgn) {
+  return (__float_as_uint(mag) & 0x7FFFFFFFu) | (__float_as_uint(sgn) & 0x80000000u);
 }
-__device__ __forceinline__ float gelu_fast(float x) {
-  float c, p;
-  gelu_parts(x, c, p);
-  return x * c;
-}
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  float c, p;
-  gelu_parts(x, c, p);
-  return fmaf(x, p, c);
+// (u0, u1) -> cdf = Phi(u), pdf = phi(u), both as pairs
+__device__ __forceinline__ void gelu_parts2(float u0, float u1, f32x2 u, f32x2& cdf, f32x2& pdf) {
+  const f32x2 a = f2_pack(fabsf(u0), fabsf(u1));
+  const f32x2 d = f2_fma(a, f2_splat(0.2316419f), f2_splat(1.0f));
+  float d0, d1, g0, g1;
+  f2_unpack(d, d0, d1);
+  const f32x2 t = f2_pack(rcp_ftz(d0), rcp_ftz(d1));
+  // phi(u) = 2^(-u^2 * log2(e)/2 + log2(1/sqrt(2 pi)))
+  const f32x2 arg = f2_fma(f2_mul(u, u), f2_splat(-0.72134752044448170368f), f2_splat(-1.3257480647361593f));
+  f2_unpack(arg, g0, g1);
+  pdf = f2_pack(ex2_ftz(g0), ex2_ftz(g1));
+  f32x2 poly = f2_fma(f2_splat(1.330274429f), t, f2_splat(-1.821255978f));
+  poly = f2_fma(poly, t, f2_splat(1.781477937f));
+  poly = f2_fma(poly, t, f2_splat(-0.356563782f));
+  poly = f2_fma(poly, t, f2_splat(0.319381530f));
+  const f32x2 h = f2_mul(f2_mul(poly, t), pdf);                      // 1 - Phi(|u|), in [0, 0.5]
+  const f32x2 g = f2_fma(h, f2_splat(-1.0f), f2_splat(0.5f));        // Phi(|u|) - 0.5
+  f2_unpack(g, g0, g1);
+  cdf = f2_add(f2_pack_u(copysign_bits(g0, u0), copysign_bits(g1, u1)), f2_splat(0.5f));
 }
 
 // ---- per-warp staging tile: 32 rows x 128 B, 16-byte units XOR-swizzled by (row & 7) -----------
@@ -232,87 +241,123 @@ __device__ __forceinline__ void stage_flush(uint8_t* stg, void* base, long long 
   }
 }
 
-// One 32-column chunk of this thread's row: acc (+bias) (+aux) -> packed 16-byte units in `stg`
-// (and `stg2` values for the GELU pre-activation). `mine` holds this row's aux units of the chunk.
-template <int EPI>
-__device__ __forceinline__ void chunk_math(float (&v)[32], const GemmTcParams& p, const float4 (&bv)[8],
+// One 32-column chunk of this thread's row as 16 packed pairs: acc (+bias) (+aux). `mine` holds
+// this row's aux units of the chunk.
+template <int EPI, bool BF16>
+__device__ __forceinline__ void chunk_math(f32x2 (&v)[16], const GemmTcParams& p, const float4 (&bv)[8],
                                            const uint4* mine /*this chunk's aux units or nullptr*/,
                                            float rscale) {
   if (EPI != FV_EPI_ACCUM && EPI != FV_EPI_DGELU) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      v[q * 4 + 0] += bv[q].x; v[q * 4 + 1] += bv[q].y; v[q * 4 + 2] += bv[q].z; v[q * 4 + 3] += bv[q].w;
+      v[q * 2] = f2_add(v[q * 2], f2_pack(bv[q].x, bv[q].y));
+      v[q * 2 + 1] = f2_add(v[q * 2 + 1], f2_pack(bv[q].z, bv[q].w));
     }
   }
   if (EPI == FV_EPI_RESIDUAL && p.row_scale != nullptr) {  // drop-path: scale the branch, not the residual
+    const f32x2 rs = f2_splat(rscale);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= rscale;
+    for (int i = 0; i < 16; ++i) v[i] = f2_mul(v[i], rs);
   }
   if (EPI == FV_EPI_RESIDUAL || EPI == FV_EPI_PATCH) {  // fp32 aux, 8 units per chunk
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      v[q * 4 + 0] += __uint_as_float(mine[q].x); v[q * 4 + 1] += __uint_as_float(mine[q].y);
-      v[q * 4 + 2] += __uint_as_float(mine[q].z); v[q * 4 + 3] += __uint_as_float(mine[q].w);
+      v[q * 2] = f2_add(v[q * 2], f2_pack_u(mine[q].x, mine[q].y));
+      v[q * 2 + 1] = f2_add(v[q * 2 + 1], f2_pack_u(mine[q].z, mine[q].w));
     }
   } else if (EPI == FV_EPI_DGELU) {
-    if (p.c_bf16) {  // bf16 gelu'(u) saved by the forward GELU epilogue, 4 units per chunk
+    if (BF16) {  // bf16 gelu'(u) saved by the forward GELU epilogue, 4 units per chunk
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t w[4] = {mine[q].x, mine[q].y, mine[q].z, mine[q].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 g = unpack_bf16(w[j]);
-          v[q * 8 + j * 2] *= g.x;
-          v[q * 8 + j * 2 + 1] *= g.y;
-        }
+        for (int j = 0; j < 4; ++j)
+          v[q * 4 + j] = f2_mul(v[q * 4 + j], f2_pack_u(w[j] << 16, w[j] & 0xFFFF0000u));
       }
     } else {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        v[q * 4 + 0] *= __uint_as_float(mine[q].x);
-        v[q * 4 + 1] *= __uint_as_float(mine[q].y);
-        v[q * 4 + 2] *= __uint_as_float(mine[q].z);
-        v[q * 4 + 3] *= __uint_as_float(mine[q].w);
+        v[q * 2] = f2_mul(v[q * 2], f2_pack_u(mine[q].x, mine[q].y));
+        v[q * 2 + 1] = f2_mul(v[q * 2 + 1], f2_pack_u(mine[q].z, mine[q].w));
       }
     }
   }
 }
 
+__device__ __forceinline__ uint32_t pack_bf16(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack_bf16(lo, hi);
+}
+
 // write this thread's 32 values of a chunk into its staging row, starting at 16-byte unit `u0`
-__device__ __forceinline__ void chunk_to_stage(const float (&v)[32], uint8_t* stg, int lane, int u0,
+__device__ __forceinline__ void chunk_to_stage(const f32x2 (&v)[16], uint8_t* stg, int lane, int u0,
                                                bool bf16) {
   if (bf16) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 w;
-      w.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-      w.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-      w.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-      w.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-      *stg_unit(stg, lane, u0 + q) = w;
-    }
+    for (int q = 0; q < 4; ++q)
+      *stg_unit(stg, lane, u0 + q) =
+          make_uint4(pack_bf16(v[q * 4]), pack_bf16(v[q * 4 + 1]), pack_bf16(v[q * 4 + 2]), pack_bf16(v[q * 4 + 3]));
   } else {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      *stg_unit(stg, lane, u0 + q) = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
-                                                __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+      uint4 w;
+      asm("mov.b64 {%0, %1}, %2;" : "=r"(w.x), "=r"(w.y) : "l"(v[q * 2]));
+      asm("mov.b64 {%0, %1}, %2;" : "=r"(w.z), "=r"(w.w) : "l"(v[q * 2 + 1]));
+      *stg_unit(stg, lane, u0 + q) = w;
     }
   }
 }
 
 // Epilogue of one 128 x 256 accumulator tile for one warp (its 32 TMEM lanes / rows).
+// Output path: each warp's staged 32-row x 128-byte segment (already in the TMA 128B-swizzle
+// layout) leaves through ONE tensor store issued by lane 0 — cp.async.bulk.tensor (plain outputs)
+// or cp.reduce.async.bulk.tensor .add (split-K weight-gradient accumulate) — instead of 8 LDS + 8
+// STG/RED per lane: ncu showed the epilogue warps, not the tensor pipe, on the critical path of the
+// K = 768 shapes, a third of their stall samples in that flush. `pending` = this warp has a store
+// in flight that may still be reading the staging tile.
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* stg, uint32_t taddr,
-                                              long long row0, int n0, int width, int lane) {
+__device__ __forceinline__ void stage_store(const GemmTcParams& p, const CUtensorMap* map, uint8_t* stg, void* base,
+                                            long long ld, const SegGeom& g, int lane, bool& pending) {
+  if (p.dbg & 1) return;
+  if (EPI == FV_EPI_PATCH || !p.tma_out) {
+    stage_flush<EPI>(stg, base, ld, p, g, lane);
+    return;
+  }
+  fence_proxy_async_smem();  // generic-proxy writes of the tile -> visible to the TMA engine
+  __syncwarp();
+  if (lane == 0) {
+    if (EPI == FV_EPI_ACCUM) {
+      tma_reduce_add_2d(map, stg, g.col0, static_cast<int>(g.row0));
+    } else {
+      tma_store_2d(map, stg, g.col0, static_cast<int>(g.row0));
+    }
+    tma_store_commit();
+  }
+  pending = true;
+}
+__device__ __forceinline__ void stage_acquire(int lane, bool& pending) {
+  if (pending) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    pending = false;
+  }
+}
+
+template <int EPI, bool BF16>
+__device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUtensorMap* map_c,
+                                              const CUtensorMap* map_aux, uint8_t* stg, uint32_t taddr,
+                                              long long row0, int n0, int width, int lane, bool& pending) {
   constexpr bool HAS_AUX_IN = (EPI == FV_EPI_RESIDUAL || EPI == FV_EPI_DGELU || EPI == FV_EPI_PATCH);
-  const bool bf16 = p.c_bf16 != 0;
-  const int seg_cols = bf16 ? 64 : 32;          // columns per 128-byte segment
-  const int chunks_per_seg = bf16 ? 2 : 1;
-  const int aux_elem = (EPI == FV_EPI_DGELU) ? (bf16 ? 2 : 4) : 4;
-  const int aux_units_per_chunk = 32 * aux_elem / 16;
+  constexpr bool bf16 = BF16;  // output type (and the type of the DGELU aux input)
+  constexpr int seg_cols = bf16 ? 64 : 32;          // columns per 128-byte segment
+  constexpr int chunks_per_seg = bf16 ? 2 : 1;
+  constexpr int aux_elem = (EPI == FV_EPI_DGELU) ? (bf16 ? 2 : 4) : 4;
+  constexpr int aux_units_per_chunk = 32 * aux_elem / 16;
   int nseg = (p.N - n0 + seg_cols - 1) / seg_cols;
   if (nseg > width / seg_cols) nseg = width / seg_cols;
 
+  if (p.dbg & 2) return;
   float rscale = 1.0f;
   if (EPI == FV_EPI_RESIDUAL && p.row_scale != nullptr) {
     const long long row = row0 + lane;  // this thread's accumulator row
@@ -326,6 +371,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
     uint4 mine[8];
     if (HAS_AUX_IN) {
       // bounce the prefetched aux segment through the staging tile so each thread gets its row
+      stage_acquire(lane, pending);
       aux_to_stage(pre, stg, lane);
       __syncwarp();
 #pragma unroll
@@ -354,62 +400,202 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, uint8_t* st
                         : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_ld_wait();
-        float v[32];
+        f32x2 v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        chunk_math<EPI>(v, p, bv, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr, rscale);
+        for (int i = 0; i < 16; ++i) v[i] = f2_pack_u(r[2 * i], r[2 * i + 1]);
+        chunk_math<EPI, BF16>(v, p, bv, HAS_AUX_IN ? &mine[c * aux_units_per_chunk] : nullptr, rscale);
         if (EPI == FV_EPI_GELU) {
           // Activation AND its derivative from the one cdf/pdf evaluation: out = u*Phi(u) goes to
           // gbuf (stored last), aux = Phi(u) + u*phi(u) replaces the pre-activation as the tensor
           // kept for the backward — the fc2 dgrad epilogue then only multiplies (FV_EPI_DGELU).
           // u is first rounded to the output type, as autocast does (fc1 emits bf16 and nn.GELU
-          // runs on that tensor): round by packing pairs (one F2FP per two elements) and
+          // runs on that tensor): round by packing the pair (one F2FP per two elements) and
           // unpacking with shifts, not one F2F per element.
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float u0 = v[i], u1 = v[i + 1];
+          for (int i = 0; i < 16; ++i) {
+            float u0, u1;
+            f2_unpack(v[i], u0, u1);
+            f32x2 u = v[i];
             if (bf16) {
-              const float2 u = unpack_bf16(pack_bf16(u0, u1));
-              u0 = u.x;
-              u1 = u.y;
+              const float2 ur = unpack_bf16(pack_bf16(u0, u1));
+              u0 = ur.x;
+              u1 = ur.y;
+              u = f2_pack(u0, u1);
             }
-            float c0, p0, c1, p1;
-            gelu_parts(u0, c0, p0);
-            gelu_parts(u1, c1, p1);
-            v[i] = fmaf(u0, p0, c0);
-            v[i + 1] = fmaf(u1, p1, c1);
+            f32x2 cdf, pdf;
+            gelu_parts2(u0, u1, u, cdf, pdf);
+            v[i] = f2_fma(u, pdf, cdf);
+            const f32x2 act = f2_mul(u, cdf);
             if (bf16) {
-              gbuf[c * 16 + (i >> 1)] = pack_bf16(u0 * c0, u1 * c1);
+              gbuf[c * 16 + i] = pack_bf16(act);
             } else {
-              gbuf[i] = __float_as_uint(u0 * c0);
-              gbuf[i + 1] = __float_as_uint(u1 * c1);
+              asm("mov.b64 {%0, %1}, %2;" : "=r"(gbuf[2 * i]), "=r"(gbuf[2 * i + 1]) : "l"(act));
             }
           }
         }
+        if (c == 0) stage_acquire(lane, pending);
         chunk_to_stage(v, stg, lane, c * (bf16 ? 4 : 8), bf16);
       }
     }
     __syncwarp();
     if (EPI == FV_EPI_GELU) {
-      stage_flush<EPI>(stg, p.aux, p.ldaux, p, go, lane);  // gelu'(u) -> aux
+      stage_store<EPI>(p, map_aux, stg, p.aux, p.ldaux, go, lane, pending);  // gelu'(u) -> aux
       __syncwarp();
+      stage_acquire(lane, pending);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         *stg_unit(stg, lane, q) = make_uint4(gbuf[q * 4], gbuf[q * 4 + 1], gbuf[q * 4 + 2], gbuf[q * 4 + 3]);
       __syncwarp();
     }
-    stage_flush<EPI>(stg, p.c, p.ldc, p, go, lane);
+    stage_store<EPI>(p, map_c, stg, p.c, p.ldc, go, lane, pending);
     __syncwarp();
   }
 }
 
-template <int EPI>
+// ---- direct epilogue: no shared-memory staging -------------------------------------------------
+// thread == accumulator row; every 32-column chunk leaves (and its aux operand arrives) as 256-bit
+// per-thread accesses, each one whole 32-byte sector of the thread's own row. The MMA's operand
+// reads keep ~3/4 of the shared-memory bandwidth busy at full rate, so the staged transpose (write
+// + read of every output byte through smem) competes with the tensor core; this path does not
+// touch shared memory at all.
+__device__ __forceinline__ void ld_v8(uint32_t (&r)[8], const void* ptr) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
+__device__ __forceinline__ void st_v8(void* ptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// store 32 columns (already packed: 16 words bf16 / 32 words fp32) of one row, clipped at N (N % 8 == 0)
+template <bool BF16>
+__device__ __forceinline__ void store_chunk(void* base, long long ld, long long row, int col0, int N,
+                                            const uint32_t* w) {
+  if (BF16) {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(base) + (row * ld + col0) * 2;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (col0 + j * 16 + 16 <= N) {
+        st_v8(dst + j * 32, w + j * 8);
+      } else if (col0 + j * 16 + 8 <= N) {
+        *reinterpret_cast<uint4*>(dst + j * 32) = make_uint4(w[j * 8], w[j * 8 + 1], w[j * 8 + 2], w[j * 8 + 3]);
+      }
+    }
+  } else {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(base) + (row * ld + col0) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col0 + j * 8 + 8 <= N) st_v8(dst + j * 32, w + j * 8);
+  }
+}
+// load the aux operand of one chunk of one row: AUX_BF16 ? 16 words : 32 words (zero past N / M)
+template <bool AUX_BF16>
+__device__ __forceinline__ void load_chunk(uint32_t* w, const void* base, long long ld, long long row, bool row_ok,
+                                           int col0, int N) {
+  constexpr int PIECES = AUX_BF16 ? 2 : 4, CPP = AUX_BF16 ? 16 : 8, ELEM = AUX_BF16 ? 2 : 4;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(base) + (row * ld + col0) * ELEM;
+#pragma unroll
+  for (int j = 0; j < PIECES; ++j) {
+    uint32_t (&dst)[8] = *reinterpret_cast<uint32_t(*)[8]>(w + j * 8);
+    if (row_ok && col0 + j * CPP + CPP <= N) {
+      ld_v8(dst, src + j * 32);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[i] = 0u;
+      if (AUX_BF16 && row_ok && col0 + j * CPP + 8 <= N) {
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(src + j * 32));
+        dst[0] = h.x; dst[1] = h.y; dst[2] = h.z; dst[3] = h.w;
+      }
+    }
+  }
+}
+
+template <int EPI, bool BF16>
+__device__ __forceinline__ void epilogue_tile_direct(const GemmTcParams& p, uint32_t taddr, long long row0, int n0,
+                                                     int width, int lane) {
+  constexpr bool HAS_AUX_IN = (EPI == FV_EPI_RESIDUAL || EPI == FV_EPI_DGELU);
+  constexpr bool AUX_BF16 = (EPI == FV_EPI_DGELU) && BF16;
+  constexpr int AUX_WORDS = AUX_BF16 ? 16 : 32;
+  const long long row = row0 + lane;
+  const bool row_ok = row < p.M;
+  int nchunk = (p.N - n0 + 31) / 32;
+  if (nchunk > width / 32) nchunk = width / 32;
+  float rscale = 1.0f;
+  if (EPI == FV_EPI_RESIDUAL && p.row_scale != nullptr) rscale = row_ok ? __ldg(p.row_scale + row / p.rows_per_scale) : 0.f;
+  uint32_t pre[HAS_AUX_IN ? AUX_WORDS : 1];
+  if (HAS_AUX_IN && nchunk > 0) load_chunk<AUX_BF16>(pre, p.aux, p.ldaux, row, row_ok, n0, p.N);
+  for (int c = 0; c < nchunk; ++c) {
+    const int col0 = n0 + c * 32;
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c * 32, r);
+    float4 bv[8];
+    if (EPI != FV_EPI_DGELU) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        bv[q] = (p.bias != nullptr && col0 + q * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint4 mine[8];
+    if (HAS_AUX_IN) {
+#pragma unroll
+      for (int q = 0; q < AUX_WORDS / 4; ++q) mine[q] = make_uint4(pre[q * 4], pre[q * 4 + 1], pre[q * 4 + 2], pre[q * 4 + 3]);
+      if (c + 1 < nchunk) load_chunk<AUX_BF16>(pre, p.aux, p.ldaux, row, row_ok, col0 + 32, p.N);  // next chunk in flight
+    }
+    tmem_ld_wait();
+    f32x2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = f2_pack_u(r[2 * i], r[2 * i + 1]);
+    chunk_math<EPI, BF16>(v, p, bv, HAS_AUX_IN ? mine : nullptr, rscale);
+    uint32_t w[BF16 ? 16 : 32];
+    if (EPI == FV_EPI_GELU) {  // see epilogue_tile: activation -> c, derivative -> aux
+      uint32_t g[BF16 ? 16 : 32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float u0, u1;
+        f2_unpack(v[i], u0, u1);
+        f32x2 u = v[i];
+        if (BF16) {
+          const float2 ur = unpack_bf16(pack_bf16(u0, u1));
+          u0 = ur.x;
+          u1 = ur.y;
+          u = f2_pack(u0, u1);
+        }
+        f32x2 cdf, pdf;
+        gelu_parts2(u0, u1, u, cdf, pdf);
+        const f32x2 grad = f2_fma(u, pdf, cdf), act = f2_mul(u, cdf);
+        if (BF16) {
+          w[i] = pack_bf16(act);
+          g[i] = pack_bf16(grad);
+        } else {
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(w[2 * i]), "=r"(w[2 * i + 1]) : "l"(act));
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(g[2 * i]), "=r"(g[2 * i + 1]) : "l"(grad));
+        }
+      }
+      if (row_ok && !(p.dbg & 1)) store_chunk<BF16>(p.aux, p.ldaux, row, col0, p.N, g);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (BF16) {
+          w[i] = pack_bf16(v[i]);
+        } else {
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(w[2 * i]), "=r"(w[2 * i + 1]) : "l"(v[i]));
+        }
+      }
+    }
+    if (row_ok && !(p.dbg & 1)) store_chunk<BF16>(p.c, p.ldc, row, col0, p.N, w);
+  }
+}
+
+template <int EPI, bool BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
                const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space
+  // known to the compiler: LDS / STS instead of generic LD / ST for every staging access
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;  // 8 x 4 KiB, 1024-byte aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -423,6 +609,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_out) {
+      tma_prefetch_desc(&tmap_c);
+      if (EPI == FV_EPI_GELU) tma_prefetch_desc(&tmap_aux);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -548,6 +738,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase = 0;
     int cs_stage = 0;
     uint32_t cs_phase = 0;
+    bool pending = false;  // a tensor store of this warp may still be reading its staging tile
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
@@ -569,7 +760,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           if (lane == 0) mbar_wait(&full_bar[cs_stage], cs_phase);  // one poller per warp
           __syncwarp();
-          if (kb % p.num_n_blocks == n_blk) {  // this CTA's share of the row block's k-slices
+          if (kb % p.num_n_blocks == n_blk && !(p.dbg & 8)) {  // this CTA's share of the row block's k-slices
             const uint8_t* sa = smem + cs_stage * STAGE_BYTES + (cp >> 5) * (64 * BK * 2) + (cp & 3) * 4;
             const int unit = (cp & 31) >> 2;
 #pragma unroll
@@ -602,12 +793,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const long long row0 = static_cast<long long>(m_blk) * BM + wq * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + half * (BN / 2);
-      epilogue_tile<EPI>(p, epi_stage + (warp - 4) * EPI_STAGE_BYTES, taddr, row0,
-                         n_blk * BN + half * (BN / 2), BN / 2, lane);
+      if (EPI != FV_EPI_ACCUM && EPI != FV_EPI_PATCH && p.direct) {
+        epilogue_tile_direct<EPI, BF16>(p, taddr, row0, n_blk * BN + half * (BN / 2), BN / 2, lane);
+      } else {
+        epilogue_tile<EPI, BF16>(p, &tmap_c, &tmap_aux, epi_stage + (warp - 4) * EPI_STAGE_BYTES, taddr, row0,
+                                 n_blk * BN + half * (BN / 2), BN / 2, lane, pending);
+      }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (pending && lane == 0) tma_store_wait_all();  // this thread's tensor stores are complete
   }
 
   tc_fence_before();
@@ -655,19 +851,43 @@ static int make_operand_map(CUtensorMap* map, const void* base, int major, int64
   return FV_OK;
 }
 
-template <int EPI>
-static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p,
-                          cudaStream_t stream) {
+// output tensor map: [rows, cols] row-major, box = 32 rows x 128 bytes, 128B swizzle (the layout
+// the epilogue warps stage their segments in)
+static int make_out_map(CUtensorMap* map, const void* base, bool bf16, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return FV_ERR_CUDA;
+  }
+  const int elem = bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(output) failed (%d): base=%p rows=%lld cols=%lld ld=%lld", static_cast<int>(r),
+              base, static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld));
+    return FV_ERR_CUDA;
+  }
+  return FV_OK;
+}
+
+template <int EPI, bool BF16>
+static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx,
+                          const GemmTcParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    FV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI>,
+    FV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, BF16>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        GEMM_SMEM_BYTES));
     configured = true;
   }
   const int total = p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  FV_CHECK_CUDA(fv::launch_pdl(gemm_tc_kernel<EPI>, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, stream, ta, tb, p));
+  FV_CHECK_CUDA(fv::launch_pdl(gemm_tc_kernel<EPI, BF16>, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, stream, ta, tb, tc, tx, p));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -675,6 +895,14 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 }  // namespace fv
 
 namespace fv {
+static int gemm_dbg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FEDVIT_GEMM_DBG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 static thread_local float* g_wgrad_colsum = nullptr;
 static thread_local const float* g_row_scale = nullptr;
 static thread_local int g_rows_per_scale = 0;
@@ -734,6 +962,14 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
   FV_CHECK_ARG(p.row_scale == nullptr || (epilogue == FV_EPI_RESIDUAL && p.rows_per_scale > 0),
                "fv_gemm_bf16: row scaling needs the residual epilogue");
   p.im2col = 0;
+  p.dbg = gemm_dbg();
+  {
+    const int64_t ce = p.c_bf16 ? 2 : 4;
+    const int64_t ae = (epilogue == FV_EPI_RESIDUAL) ? 4 : ce;
+    bool ok = (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (ldc * ce) % 32 == 0;
+    if (aux != nullptr) ok = ok && (reinterpret_cast<uintptr_t>(aux) & 31) == 0 && (ldaux * ae) % 32 == 0;
+    p.direct = (ok && (p.dbg & 4)) ? 1 : 0;
+  }
   p.gw = p.gh = p.chans = p.ph_per_tile = p.tiles_per_img = 0;
   FV_CHECK_ARG(p.colsum == nullptr || (epilogue == FV_EPI_ACCUM && a_major == FV_MAJOR_MN),
                "fv_gemm_bf16: bias-gradient fusion needs the weight-gradient mode");
@@ -744,14 +980,28 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
   rc = make_operand_map(&tb, b, b_major, n, k, ldb, BN);
   if (rc != FV_OK) return rc;
 
+  CUtensorMap tc = ta, tx = ta;  // placeholders unless the output path uses them
+  p.tma_out = (epilogue != FV_EPI_PATCH && !(p.dbg & 16)) ? 1 : 0;
+  if (p.tma_out) {
+    rc = make_out_map(&tc, c, p.c_bf16 != 0, m, n, ldc);
+    if (rc != FV_OK) return rc;
+    if (epilogue == FV_EPI_GELU) {
+      rc = make_out_map(&tx, aux, p.c_bf16 != 0, m, n, ldaux);
+      if (rc != FV_OK) return rc;
+    }
+  }
+
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epilogue) {
-    case FV_EPI_NONE: return launch_gemm_tc<FV_EPI_NONE>(ta, tb, p, st);
-    case FV_EPI_RESIDUAL: return launch_gemm_tc<FV_EPI_RESIDUAL>(ta, tb, p, st);
-    case FV_EPI_GELU: return launch_gemm_tc<FV_EPI_GELU>(ta, tb, p, st);
-    case FV_EPI_DGELU: return launch_gemm_tc<FV_EPI_DGELU>(ta, tb, p, st);
-    case FV_EPI_ACCUM: return launch_gemm_tc<FV_EPI_ACCUM>(ta, tb, p, st);
-    case FV_EPI_PATCH: return launch_gemm_tc<FV_EPI_PATCH>(ta, tb, p, st);
+    case FV_EPI_NONE:
+      return p.c_bf16 ? launch_gemm_tc<FV_EPI_NONE, true>(ta, tb, tc, tx, p, st) : launch_gemm_tc<FV_EPI_NONE, false>(ta, tb, tc, tx, p, st);
+    case FV_EPI_RESIDUAL: return launch_gemm_tc<FV_EPI_RESIDUAL, false>(ta, tb, tc, tx, p, st);
+    case FV_EPI_GELU:
+      return p.c_bf16 ? launch_gemm_tc<FV_EPI_GELU, true>(ta, tb, tc, tx, p, st) : launch_gemm_tc<FV_EPI_GELU, false>(ta, tb, tc, tx, p, st);
+    case FV_EPI_DGELU:
+      return p.c_bf16 ? launch_gemm_tc<FV_EPI_DGELU, true>(ta, tb, tc, tx, p, st) : launch_gemm_tc<FV_EPI_DGELU, false>(ta, tb, tc, tx, p, st);
+    case FV_EPI_ACCUM: return launch_gemm_tc<FV_EPI_ACCUM, false>(ta, tb, tc, tx, p, st);
+    case FV_EPI_PATCH: return launch_gemm_tc<FV_EPI_PATCH, false>(ta, tb, tc, tx, p, st);
   }
   return FV_ERR_INVALID_ARG;
 }
@@ -812,6 +1062,9 @@ extern "C" int fv_patch_embed_tf32(const float* img, const float* weight, const 
   p.colsum = nullptr;
   p.row_scale = nullptr;
   p.rows_per_scale = 0;
+  p.dbg = 0;
+  p.direct = 0;
+  p.tma_out = 0;
 
   CUtensorMap ta, tb;
   {  // image viewed as (px, py, pw, ph, b*c); strides in bytes for dims 1..4
@@ -842,7 +1095,7 @@ extern "C" int fv_patch_embed_tf32(const float* img, const float* weight, const 
       return FV_ERR_CUDA;
     }
   }
-  return launch_gemm_tc<FV_EPI_PATCH>(ta, tb, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm_tc<FV_EPI_PATCH, false>(ta, tb, ta, ta, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fv_linear_residual_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias,
