@@ -58,7 +58,10 @@ struct GemmTcParams {
   int ph_per_tile, tiles_per_img;
   int tma_out;  // outputs leave through TMA tensor stores (everything but the PATCH row remap)
   int direct;  // epilogue without smem staging (needs 32-byte aligned rows of c / aux)
-  int dbg;  // FEDVIT_GEMM_DBG (measurement only): 1 = epilogue without global stores, 2 = no epilogue work
+  // FEDVIT_GEMM_DBG (measurement / test switches): 1 = epilogue without global stores, 2 = no epilogue work,
+  // 4 = direct (unstaged) epilogue, 8 = bias-gradient protocol without the reads, 16 = LSU flush instead of
+  // TMA stores, 32 = never use the CTA-pair kernel, 64 = use it for every legal shape (small test problems)
+  int dbg;
 };
 
 // PATCH epilogue row mapping: local row r of M tile m_blk -> (valid?, global output row, pos row)
@@ -815,6 +818,159 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair kernel: 256 x 256 output tile per cluster of two CTAs (tcgen05.mma.cta_group::2)
+// ---------------------------------------------------------------------------------------------
+// Each CTA loads its 128 rows of A and its 128-column HALF of B (32 KiB per k-block instead of the
+// 48 KiB a single-CTA 128 x 256 tile needs: one third less L2 -> SM traffic and shared-memory
+// operand bandwidth, and a 6-deep instead of 4-deep ring in the same shared memory), the leader
+// CTA's MMA thread issues one M = 256 instruction for the pair, and each CTA drains the 128
+// accumulator rows that live in its own tensor memory with the epilogue above.
+//   full_bar[s]   leader only: 1 arrival (leader's expect_tx of both CTAs' bytes) + complete_tx from both
+//   empty_bar[s]  per CTA: tcgen05.commit multicast to both CTAs
+//   tmem_full[a]  per CTA: commit multicast;   tmem_empty[a]  leader only: one arrival per epilogue warp of both CTAs
+constexpr int STAGES2 = 6;
+constexpr int HALF_BN = BN / 2;
+constexpr int B2_STAGE_BYTES = HALF_BN * BK * 2;             // 16 KiB
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;  // 32 KiB
+static_assert(STAGES2 * STAGE2_BYTES == STAGES * STAGE_BYTES, "both kernels share the shared-memory budget");
+
+template <int EPI, bool BF16>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
+                const GemmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* epi_stage = smem + STAGES2 * STAGE2_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tmem_full = empty_bar + STAGES2;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+    if (EPI == FV_EPI_GELU) tma_prefetch_desc(&tmap_aux);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
+  const int total_tiles = num_m2 * p.num_n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------- TMA producer (both CTAs) -------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m2 = tile / p.num_n_blocks;
+      const int n_blk = tile - m2 * p.num_n_blocks;
+      const int row_a = m2 * 2 * BM + static_cast<int>(rank) * BM;
+      const int row_b = n_blk * BN + static_cast<int>(rank) * HALF_BN;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+        uint8_t* sa = smem + stage * STAGE2_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, row_a);  // A is K-major on this path
+        if (p.b_major == FV_MAJOR_K) {
+          tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
+        } else {
+#pragma unroll
+          for (int j = 0; j < HALF_BN / 64; ++j)
+            tma_load_2d_pair(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], row_b + j * 64, kb * BK);
+        }
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------- MMA issuer (leader CTA only) ---------------------------
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(kFmtBF16, FV_MAJOR_K, p.b_major, 2 * BM, BN);
+      const uint32_t b_lbo = p.b_major == FV_MAJOR_K ? 16 : 64 * BK * 2;
+      const uint32_t b_kstep = (p.b_major == FV_MAJOR_K ? 32 : 2048) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_pair(tmem_d, da + k * 2, db + k * b_kstep, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[acc]);  // accumulator complete -> both CTAs' epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------- epilogue (both CTAs, own 128 rows) ----------------------
+    const int wq = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    bool pending = false;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m2 = tile / p.num_n_blocks;
+      const int n_blk = tile - m2 * p.num_n_blocks;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const long long row0 = static_cast<long long>(m2) * 2 * BM + rank * BM + wq * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + half * (BN / 2);
+      epilogue_tile<EPI, BF16>(p, &tmap_c, &tmap_aux, epi_stage + (warp - 4) * EPI_STAGE_BYTES, taddr, row0,
+                               n_blk * BN + half * (BN / 2), BN / 2, lane, pending);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (pending && lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs / remote arrivals are in flight
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static int make_operand_map(CUtensorMap* map, const void* base, int major, int64_t rows, int64_t k,
@@ -888,6 +1044,24 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   const int total = p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
   FV_CHECK_CUDA(fv::launch_pdl(gemm_tc_kernel<EPI, BF16>, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, stream, ta, tb, tc, tx, p));
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+template <int EPI, bool BF16>
+static int launch_gemm_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx,
+                           const GemmTcParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    FV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GEMM_SMEM_BYTES));
+    configured = true;
+  }
+  const int total = static_cast<int>(ceil_div(p.M, 2 * BM)) * p.num_n_blocks;
+  int clusters = num_sms() / 2;
+  if (clusters > total) clusters = total;
+  FV_CHECK_CUDA(fv::launch_pdl_cluster(gemm_tc2_kernel<EPI, BF16>, dim3(2 * clusters), dim3(GEMM_THREADS),
+                                       GEMM_SMEM_BYTES, stream, 2u, ta, tb, tc, tx, p));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -992,6 +1166,30 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
   }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // CTA-pair kernel (256 x 256 tiles): forward / dgrad shapes with enough tiles to fill the pairs
+  const bool pair = a_major == FV_MAJOR_K && split_k == 1 && p.tma_out && !(p.dbg & 32) &&
+                    (epilogue == FV_EPI_NONE || epilogue == FV_EPI_RESIDUAL || epilogue == FV_EPI_GELU ||
+                     epilogue == FV_EPI_DGELU) &&
+                    (ceil_div(m, 2 * BM) * p.num_n_blocks >= num_sms() / 2 || (p.dbg & 64));
+  if (pair) {
+    // B map box: this CTA's 128-row half (K-major) — the MN-major map already uses 64-column boxes
+    if (b_major == FV_MAJOR_K) {
+      rc = make_operand_map(&tb, b, b_major, n, k, ldb, HALF_BN);
+      if (rc != FV_OK) return rc;
+    }
+    switch (epilogue) {
+      case FV_EPI_NONE:
+        return p.c_bf16 ? launch_gemm_tc2<FV_EPI_NONE, true>(ta, tb, tc, tx, p, st)
+                        : launch_gemm_tc2<FV_EPI_NONE, false>(ta, tb, tc, tx, p, st);
+      case FV_EPI_RESIDUAL: return launch_gemm_tc2<FV_EPI_RESIDUAL, false>(ta, tb, tc, tx, p, st);
+      case FV_EPI_GELU:
+        return p.c_bf16 ? launch_gemm_tc2<FV_EPI_GELU, true>(ta, tb, tc, tx, p, st)
+                        : launch_gemm_tc2<FV_EPI_GELU, false>(ta, tb, tc, tx, p, st);
+      case FV_EPI_DGELU:
+        return p.c_bf16 ? launch_gemm_tc2<FV_EPI_DGELU, true>(ta, tb, tc, tx, p, st)
+                        : launch_gemm_tc2<FV_EPI_DGELU, false>(ta, tb, tc, tx, p, st);
+    }
+  }
   switch (epilogue) {
     case FV_EPI_NONE:
       return p.c_bf16 ? launch_gemm_tc<FV_EPI_NONE, true>(ta, tb, tc, tx, p, st) : launch_gemm_tc<FV_EPI_NONE, false>(ta, tb, tc, tx, p, st);
