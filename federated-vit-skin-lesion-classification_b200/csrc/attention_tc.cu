@@ -286,23 +286,23 @@ struct AttnBwdParams {
   int N, H, kw;
   float scale;
   const float* lse;
-  const float* delta;
+  const __nv_bfloat16* o;     // forward output  [B, N, H*64]
+  const __nv_bfloat16* dout;  // its gradient    [B, N, H*64]
   __nv_bfloat16* dqkv;
 };
 
 __global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                   const __grid_constant__ CUtensorMap tmap_o, const AttnBwdParams p) {
+                   const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space
   // known to the compiler: LDS / STS instead of generic LD / ST for every staging access
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                  // 2 tiles
   uint8_t* sdO = sQ + 2 * ATB_TILE;    // 2 tiles
-  uint8_t* sO = sdO + 2 * ATB_TILE;    // 2 tiles (forward output, only for delta = rowsum(dO * O))
-  uint8_t* sK = sO + 2 * ATB_TILE;
-  uint8_t* sV = sK + ATB_TILE;
-  uint8_t* sP = sV + ATB_TILE;         // 2 column blocks of 64 keys
+  uint8_t* sK = sdO + 2 * ATB_TILE;    // 2 tiles: both key blocks are fetched up front
+  uint8_t* sV = sK + 2 * ATB_TILE;     // 2 tiles
+  uint8_t* sP = sV + 2 * ATB_TILE;     // 2 column blocks of 64 keys
   uint8_t* sdS = sP + 2 * ATB_TILE;    // 2 column blocks
   float* sDelta = reinterpret_cast<float*>(sdS + 2 * ATB_TILE);  // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
@@ -323,7 +323,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
-    tma_prefetch_desc(&tmap_o);
     mbar_init(bar_q, 1);
     mbar_init(bar_kv, 1);
     mbar_init(bar_s, 1);
@@ -342,47 +341,62 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 
   if (warp == 8 && lane == 0) {
     // ------------------------------ TMA + MMA issue ------------------------------------------
-    mbar_expect_tx(bar_q, nqt * 3 * ATB_TILE);
+    // everything one (batch, head) needs is fetched up front: Q / dO tiles and the first key block
+    // on bar_q, the second key block on bar_kv (it is not needed before the third MMA 1)
+    mbar_expect_tx(bar_q, (nqt * 2 + 2) * ATB_TILE);
     for (int t = 0; t < nqt; ++t) {
       tma_load_3d(sQ + t * ATB_TILE, &tmap_qkv, bar_q, h * 64, t * 128, b);
       tma_load_3d(sdO + t * ATB_TILE, &tmap_do, bar_q, h * 64, t * 128, b);
-      tma_load_3d(sO + t * ATB_TILE, &tmap_o, bar_q, h * 64, t * 128, b);
+    }
+    tma_load_3d(sK, &tmap_qkv, bar_q, hd + h * 64, 0, b);
+    tma_load_3d(sV, &tmap_qkv, bar_q, 2 * hd + h * 64, 0, b);
+    if (nkb > 1) {
+      mbar_expect_tx(bar_kv, 2 * ATB_TILE);
+      tma_load_3d(sK + ATB_TILE, &tmap_qkv, bar_kv, hd + h * 64, 128, b);
+      tma_load_3d(sV + ATB_TILE, &tmap_qkv, bar_kv, 2 * hd + h * 64, 128, b);
     }
     const uint32_t id_dvk = make_idesc(kFmtBF16, 1, 1, 128, 64);  // A MN-major (P^T / dS^T), B MN-major
     const uint32_t id_dq = make_idesc(kFmtBF16, 0, 1, 128, 64);   // A K-major (dS), B MN-major (K)
-    int it = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      if (kb > 0) mbar_wait(bar_kvfree, (kb - 1) & 1);  // dK/dV read out, K/V tiles free
-      mbar_expect_tx(bar_kv, 2 * ATB_TILE);
-      tma_load_3d(sK, &tmap_qkv, bar_kv, hd + h * 64, kb * 128, b);
-      tma_load_3d(sV, &tmap_qkv, bar_kv, 2 * hd + h * 64, kb * 128, b);
-      if (kb == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv, kb & 1);
+    // MMA 1 of (key block, query tile): scores and dP; contraction over the 64 head dims
+    auto issue_mma1 = [&](int kb, int qt) {
       int kwb = p.kw - kb * 128;
       if (kwb > 128) kwb = 128;
       const uint32_t id_s = make_idesc(kFmtBF16, 0, 0, 128, kwb);
-      const uint64_t dK_k = make_smem_desc_sw128(smem_u32(sK), 16, 1024);        // K-major view
-      const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
-      const uint64_t dK_mn = make_smem_desc_sw128(smem_u32(sK), ATB_TILE, 1024);  // MN-major view
-      // MMA 1 of a query tile: scores and dP; contraction over the 64 head dims
-      auto issue_mma1 = [&](int qt) {
-        const uint64_t dQ_k = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), 16, 1024);
-        const uint64_t dO_k = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), 16, 1024);
+      const uint64_t dK_k = make_smem_desc_sw128(smem_u32(sK + kb * ATB_TILE), 16, 1024);
+      const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV + kb * ATB_TILE), 16, 1024);
+      const uint64_t dQ_k = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), 16, 1024);
+      const uint64_t dO_k = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_S, dQ_k + k * 2, dK_k + k * 2, id_s, k > 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_S, dQ_k + k * 2, dK_k + k * 2, id_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_DP, dO_k + k * 2, dV_k + k * 2, id_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s);
-      };
-      tc_fence_after();
-      issue_mma1(0);
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_DP, dO_k + k * 2, dV_k + k * 2, id_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    };
+    mbar_wait(bar_q, 0);
+    tc_fence_after();
+    issue_mma1(0, 0);
+    int it = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      int kwb = p.kw - kb * 128;
+      if (kwb > 128) kwb = 128;
+      const uint64_t dK_mn = make_smem_desc_sw128(smem_u32(sK + kb * ATB_TILE), ATB_TILE, 1024);  // MN-major view
       for (int qt = 0; qt < nqt; ++qt, ++it) {
         const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), ATB_TILE, 1024);
         const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), ATB_TILE, 1024);
         mbar_wait(bar_p, it & 1);  // P / dS tiles written, S / dP consumed
         tc_fence_after();
-        // the next tile's scores go first so its softmax math overlaps this tile's MMA 2
-        if (qt + 1 < nqt) issue_mma1(qt + 1);
+        // the next (key block, query tile)'s scores go first so its softmax math overlaps this MMA 2
+        if (qt + 1 < nqt) {
+          issue_mma1(kb, qt + 1);
+        } else if (kb + 1 < nkb) {
+          mbar_wait(bar_kv, 0);
+          tc_fence_after();
+          issue_mma1(kb + 1, 0);
+        }
+        if (qt == 0 && kb > 0) {
+          mbar_wait(bar_kvfree, (kb - 1) & 1);  // the previous key block's dK / dV have left TMEM
+          tc_fence_after();
+        }
         // MMA 2: contraction over the 128 queries (dV, dK) and over the block's keys (dQ)
         const uint64_t dP_mn = make_smem_desc_sw128(smem_u32(sP), ATB_TILE, 1024);
         const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), ATB_TILE, 1024);
@@ -440,22 +454,30 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       __syncwarp();
     };
 
-    // delta[q] = sum_d dO[q,d] * O[q,d] for query tile `hf`, straight from the swizzled smem tiles
-    mbar_wait(bar_q, 0);
+    // delta[q] = sum_d dO[q,d] * O[q,d] for query tile `hf`: each thread reads its row of O and dO
+    // (one 128-byte line each) straight from global memory while the TMA loads are in flight —
+    // O never occupies shared memory. The two LSE values a thread needs live in registers.
+    float lse2[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) lse2[t] = (t * 128 + r < p.N) ? __ldg(lse_bh + t * 128 + r) * ATC_LOG2E : INFINITY;
     if (hf < nqt) {
-      const uint8_t* orow = sO + hf * ATB_TILE + r * 128;
-      const uint8_t* grow = sdO + hf * ATB_TILE + r * 128;
+      const int q = hf * 128 + r;
       float acc = 0.f;
+      if (q < p.N) {
+        const long long off = (static_cast<long long>(b) * p.N + q) * hd + h * 64;
+        const uint4* orow = reinterpret_cast<const uint4*>(p.o + off);
+        const uint4* grow = reinterpret_cast<const uint4*>(p.dout + off);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint4 a = *reinterpret_cast<const uint4*>(orow + ((u ^ (r & 7)) << 4));
-        const uint4 g = *reinterpret_cast<const uint4*>(grow + ((u ^ (r & 7)) << 4));
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+        for (int u = 0; u < 8; ++u) {
+          const uint4 a = __ldg(orow + u);
+          const uint4 g = __ldg(grow + u);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 af = unpack_bf16(aw[j]), gf = unpack_bf16(gw[j]);
-          acc = fmaf(af.x, gf.x, acc);
-          acc = fmaf(af.y, gf.y, acc);
+          for (int j = 0; j < 4; ++j) {
+            const float2 af = unpack_bf16(aw[j]), gf = unpack_bf16(gw[j]);
+            acc = fmaf(af.x, gf.x, acc);
+            acc = fmaf(af.y, gf.y, acc);
+          }
         }
       }
       sDelta[hf * 128 + r] = acc;
@@ -465,8 +487,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     int it = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       for (int qt = 0; qt < nqt; ++qt, ++it) {
-        const int q = qt * 128 + r;
-        const float l2 = q < p.N ? lse_bh[q] * ATC_LOG2E : INFINITY;
+        const float l2 = lse2[qt];
         const float dl = sDelta[qt * 128 + r];
         mbar_wait(bar_s, it & 1);
         tc_fence_after();
@@ -562,21 +583,20 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
   p.kw = static_cast<int>((tokens + 15) / 16 * 16);
   p.scale = scale;
   p.lse = lse;
-  p.delta = nullptr;  // computed in-kernel from the O / dO tiles
+  p.o = reinterpret_cast<const __nv_bfloat16*>(out);
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  CUtensorMap mq, mdo, mo;
+  CUtensorMap mq, mdo;
   int rc = make_tok_map(&mq, qkv, batch, tokens, 3 * heads * 64);
   if (rc != FV_OK) return rc;
   rc = make_tok_map(&mdo, dout, batch, tokens, heads * 64);
-  if (rc != FV_OK) return rc;
-  rc = make_tok_map(&mo, out, batch, tokens, heads * 64);
   if (rc != FV_OK) return rc;
   static bool configured = false;
   if (!configured) {
     FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM));
     configured = true;
   }
-  FV_CHECK_CUDA(fv::launch_pdl(attn_tc_bwd_kernel, dim3(static_cast<unsigned>(batch * heads)), dim3(ATB_THREADS), ATB_SMEM, stream, mq, mdo, mo, p));
+  FV_CHECK_CUDA(fv::launch_pdl(attn_tc_bwd_kernel, dim3(static_cast<unsigned>(batch * heads)), dim3(ATB_THREADS), ATB_SMEM, stream, mq, mdo, p));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

@@ -7,6 +7,8 @@
 // Algorithmic bytes per row of D columns:
 //   fwd: 4D (x) + sizeof(y)·D + 8 (mean,rstd)          bwd: sizeof(dy)·D + 4D (x) + 4D (dres)
 //                                                           + 4D (dx) [+ 2D dx_lp] + 8
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fv {
@@ -84,8 +86,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 constexpr int LNB_THREADS = 256;
 constexpr int LNB_ROWS = 4;  // rows in flight per CTA (one per warp pair)
 
-template <int NV, bool DY_BF16>
-__global__ void __launch_bounds__(LNB_THREADS, 3)
+template <int NV, bool DY_BF16, int MINB>
+__global__ void __launch_bounds__(LNB_THREADS, MINB)
 layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ dres,
@@ -114,10 +116,19 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
   // slot+1, 64 threads): no CTA-wide barrier inside the loop, so pairs overlap each other's latency
   for (long long row = first + slot; row < rows; row += stride) {
     const bool live = true;
-    float4 xh[NV], gy[NV];
+    float4 xh[NV], gy[NV], rr[NV];
     float s1 = 0.f, s2 = 0.f;
     float mu = 0.f, rs = 0.f;
     if (live) {
+      // the residual-stream gradient is only needed after the row reduction, but its load is issued
+      // here with the x / dy loads: one round trip to HBM per row instead of two
+      if (dres != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = t64 + 64 * i;
+          if (c < nvec) rr[i] = __ldcs(reinterpret_cast<const float4*>(dres + row * cols) + c);
+        }
+      }
       mu = mean[row];
       rs = rstd[row];
       const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
@@ -167,8 +178,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x,
           o.z = rs * (gy[i].z - s1 - xh[i].z * s2);
           o.w = rs * (gy[i].w - s1 - xh[i].w * s2);
           if (dres != nullptr) {
-            const float4 r = __ldcs(reinterpret_cast<const float4*>(dres + row * cols) + c);
-            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w;
           }
           reinterpret_cast<float4*>(dx + row * cols)[c] = o;
           if (dx_lp != nullptr) {
@@ -252,15 +262,26 @@ extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, co
   FV_CHECK_ARG(lp_row_scale == nullptr || (rows_per_scale > 0 && dx_lp != nullptr),
                "fv_layernorm_bwd: lp_row_scale needs dx_lp and rows_per_scale > 0");
   if (rows == 0) return FV_OK;
+  static int minb = -1;
+  if (minb < 0) {
+    const char* e = getenv("FEDVIT_LN_MINB");
+    minb = e ? atoi(e) : 3;
+  }
   int64_t want = ceil_div(rows, LNB_ROWS);
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 3;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * minb;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   const size_t smem = 2 * LNB_ROWS * cols * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(dx_lp);
 #define FV_LN_BWD(NV, BF)                                                                        \
-  FV_CHECK_CUDA(fv::launch_pdl(layernorm_bwd_kernel<NV, BF>, dim3(grid), dim3(LNB_THREADS), smem, st, dy, x, gamma, mean, rstd, dres, dx, \
-                                                                lp, dgamma, dbeta, rows, (int)cols, lp_row_scale, (int)rows_per_scale))
+  do {                                                                                           \
+    if (minb == 2)                                                                               \
+      FV_CHECK_CUDA(fv::launch_pdl(layernorm_bwd_kernel<NV, BF, 2>, dim3(grid), dim3(LNB_THREADS), smem, st, dy, x, gamma, mean, rstd, dres, dx, \
+                                   lp, dgamma, dbeta, rows, (int)cols, lp_row_scale, (int)rows_per_scale)); \
+    else                                                                                         \
+      FV_CHECK_CUDA(fv::launch_pdl(layernorm_bwd_kernel<NV, BF, 3>, dim3(grid), dim3(LNB_THREADS), smem, st, dy, x, gamma, mean, rstd, dres, dx, \
+                                   lp, dgamma, dbeta, rows, (int)cols, lp_row_scale, (int)rows_per_scale)); \
+  } while (0)
 #define FV_LN_BWD_NV(NV)                          \
   do {                                            \
     if (dy_dtype == FV_BF16) FV_LN_BWD(NV, true); \
