@@ -278,12 +278,13 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
 //   separate pass over HBM).
 // Q / dO tiles double as A operands (K-major) and B operands (MN-major); K / V likewise — every
 // tile is loaded once per (batch, head) and nothing is transposed or re-materialised.
-constexpr int ATB_THREADS = 320;  // warps 0-7 math, warp 8 TMA+MMA issue, warp 9 TMEM alloc
+constexpr int ATB_THREADS = 320;  // warps 0-7 math, warp 8 MMA issue, warp 9 TMEM alloc + TMA producer
 constexpr int ATB_TILE = 128 * 128;  // bytes of one [128 x 64] bf16 tile
-constexpr int ATB_SMEM = 12 * ATB_TILE + 1024 + 1024 + 128;  // Q0 Q1 dO0 dO1 O0 O1 K V P(2) dS(2) + delta[256]
+constexpr int ATB_SMEM = 12 * ATB_TILE + 1024 + 2048 + 256;  // Q(2) dO(2) K(2) V(2) P(2) dS(2) + delta[2][256] + barriers
 
 struct AttnBwdParams {
   int N, H, kw;
+  int items;  // batch * heads
   float scale;
   const float* lse;
   const __nv_bfloat16* o;     // forward output  [B, N, H*64]
@@ -294,41 +295,49 @@ struct AttnBwdParams {
 __global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const AttnBwdParams p) {
+  // Persistent: one CTA per SM walks (batch, head) items; barriers, tensor memory and descriptors
+  // are set up once, and the operand tiles of item i+1 are fetched (by a dedicated producer thread)
+  // as soon as the last MMA that reads the corresponding tile of item i has retired — K0/V0 after
+  // the first key block, Q0/dO0 one iteration before the end — so the next item's first MMA never
+  // waits for a cold TMA round trip. (ncu on the one-CTA-per-item version: tensor pipe 16 % active,
+  // every CTA paying launch + allocation + load latency with nothing to overlap them: 192 KB of
+  // shared memory and all 512 TMEM columns allow only one CTA per SM.)
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space
   // known to the compiler: LDS / STS instead of generic LD / ST for every staging access
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                  // 2 tiles
   uint8_t* sdO = sQ + 2 * ATB_TILE;    // 2 tiles
-  uint8_t* sK = sdO + 2 * ATB_TILE;    // 2 tiles: both key blocks are fetched up front
+  uint8_t* sK = sdO + 2 * ATB_TILE;    // 2 tiles (both key blocks)
   uint8_t* sV = sK + 2 * ATB_TILE;     // 2 tiles
   uint8_t* sP = sV + 2 * ATB_TILE;     // 2 column blocks of 64 keys
   uint8_t* sdS = sP + 2 * ATB_TILE;    // 2 column blocks
-  float* sDelta = reinterpret_cast<float*>(sdS + 2 * ATB_TILE);  // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* bar_kv = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_p = bars + 3;
-  uint64_t* bar_m2 = bars + 4;
-  uint64_t* bar_kvfree = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* sDelta = reinterpret_cast<float*>(sdS + 2 * ATB_TILE);  // [2 items][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 512);
+  uint64_t* bar_ld = bars + 0;     // [3] loaded: {Q0 dO0 K0 V0}, {Q1 dO1}, {K1 V1}
+  uint64_t* bar_free = bars + 3;   // [4] last reader retired: {K0 V0}, {Q0 dO0}, {K1 V1}, {Q1 dO1}
+  uint64_t* bar_s = bars + 7;
+  uint64_t* bar_p = bars + 8;
+  uint64_t* bar_m2 = bars + 9;
+  uint64_t* bar_kvfree = bars + 10;
+  uint64_t* bar_dqfree = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int nqt = (p.N + 127) >> 7;
-  const int nkb = (p.kw + 127) >> 7;
+  const int nt = (p.N + 127) >> 7;  // query tiles == key blocks (1 or 2)
   const int hd = p.H * 64;
+  const int nitems = p.items;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_kv, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&bar_ld[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_free[i], 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 256);
     mbar_init(bar_m2, 1);
     mbar_init(bar_kvfree, 256);
+    mbar_init(bar_dqfree, 256);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -339,22 +348,34 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   pdl_wait();  // nothing above touches memory another kernel produced
   constexpr uint32_t T_S = 0, T_DP = 128, T_DK = 256, T_DV = 320, T_DQ = 384;
 
-  if (warp == 8 && lane == 0) {
-    // ------------------------------ TMA + MMA issue ------------------------------------------
-    // everything one (batch, head) needs is fetched up front: Q / dO tiles and the first key block
-    // on bar_q, the second key block on bar_kv (it is not needed before the third MMA 1)
-    mbar_expect_tx(bar_q, (nqt * 2 + 2) * ATB_TILE);
-    for (int t = 0; t < nqt; ++t) {
-      tma_load_3d(sQ + t * ATB_TILE, &tmap_qkv, bar_q, h * 64, t * 128, b);
-      tma_load_3d(sdO + t * ATB_TILE, &tmap_do, bar_q, h * 64, t * 128, b);
+  if (warp == 9 && lane == 0) {
+    // ------------------------------ TMA producer ----------------------------------------------
+    int n = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
+      const int b = item / p.H, h = item % p.H;
+      const uint32_t prev = (n - 1) & 1;
+      // a barrier is re-armed only after its previous phase is known complete: the tiles' last
+      // readers of item n-1 have retired, so their loads (that phase) finished long ago
+      if (n > 0) mbar_wait(&bar_free[0], prev);
+      mbar_expect_tx(&bar_ld[0], 4 * ATB_TILE);
+      tma_load_3d(sK, &tmap_qkv, &bar_ld[0], hd + h * 64, 0, b);
+      tma_load_3d(sV, &tmap_qkv, &bar_ld[0], 2 * hd + h * 64, 0, b);
+      if (n > 0) mbar_wait(&bar_free[1], prev);
+      tma_load_3d(sQ, &tmap_qkv, &bar_ld[0], h * 64, 0, b);
+      tma_load_3d(sdO, &tmap_do, &bar_ld[0], h * 64, 0, b);
+      if (nt > 1) {
+        if (n > 0) mbar_wait(&bar_free[3], prev);
+        mbar_expect_tx(&bar_ld[1], 2 * ATB_TILE);
+        tma_load_3d(sQ + ATB_TILE, &tmap_qkv, &bar_ld[1], h * 64, 128, b);
+        tma_load_3d(sdO + ATB_TILE, &tmap_do, &bar_ld[1], h * 64, 128, b);
+        if (n > 0) mbar_wait(&bar_free[2], prev);
+        mbar_expect_tx(&bar_ld[2], 2 * ATB_TILE);
+        tma_load_3d(sK + ATB_TILE, &tmap_qkv, &bar_ld[2], hd + h * 64, 128, b);
+        tma_load_3d(sV + ATB_TILE, &tmap_qkv, &bar_ld[2], 2 * hd + h * 64, 128, b);
+      }
     }
-    tma_load_3d(sK, &tmap_qkv, bar_q, hd + h * 64, 0, b);
-    tma_load_3d(sV, &tmap_qkv, bar_q, 2 * hd + h * 64, 0, b);
-    if (nkb > 1) {
-      mbar_expect_tx(bar_kv, 2 * ATB_TILE);
-      tma_load_3d(sK + ATB_TILE, &tmap_qkv, bar_kv, hd + h * 64, 128, b);
-      tma_load_3d(sV + ATB_TILE, &tmap_qkv, bar_kv, 2 * hd + h * 64, 128, b);
-    }
+  } else if (warp == 8 && lane == 0) {
+    // ------------------------------ MMA issue --------------------------------------------------
     const uint32_t id_dvk = make_idesc(kFmtBF16, 1, 1, 128, 64);  // A MN-major (P^T / dS^T), B MN-major
     const uint32_t id_dq = make_idesc(kFmtBF16, 0, 1, 128, 64);   // A K-major (dS), B MN-major (K)
     // MMA 1 of (key block, query tile): scores and dP; contraction over the 64 head dims
@@ -372,46 +393,66 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_DP, dO_k + k * 2, dV_k + k * 2, id_s, k > 0 ? 1u : 0u);
       umma_commit(bar_s);
     };
-    mbar_wait(bar_q, 0);
-    tc_fence_after();
-    issue_mma1(0, 0);
-    int it = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      int kwb = p.kw - kb * 128;
-      if (kwb > 128) kwb = 128;
-      const uint64_t dK_mn = make_smem_desc_sw128(smem_u32(sK + kb * ATB_TILE), ATB_TILE, 1024);  // MN-major view
-      for (int qt = 0; qt < nqt; ++qt, ++it) {
-        const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), ATB_TILE, 1024);
-        const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), ATB_TILE, 1024);
-        mbar_wait(bar_p, it & 1);  // P / dS tiles written, S / dP consumed
+    int it = 0;   // (key block, query tile) iterations so far, over all items
+    int kvn = 0;  // key blocks so far
+    int n = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
+      const uint32_t ph = n & 1;
+      if (n == 0) {
+        mbar_wait(&bar_ld[0], 0);
         tc_fence_after();
-        // the next (key block, query tile)'s scores go first so its softmax math overlaps this MMA 2
-        if (qt + 1 < nqt) {
-          issue_mma1(kb, qt + 1);
-        } else if (kb + 1 < nkb) {
-          mbar_wait(bar_kv, 0);
+        issue_mma1(0, 0);
+      }
+      const bool has_next = item + static_cast<int>(gridDim.x) < nitems;
+      for (int kb = 0; kb < nt; ++kb, ++kvn) {
+        int kwb = p.kw - kb * 128;
+        if (kwb > 128) kwb = 128;
+        const uint64_t dK_mn = make_smem_desc_sw128(smem_u32(sK + kb * ATB_TILE), ATB_TILE, 1024);  // MN-major view
+        for (int qt = 0; qt < nt; ++qt, ++it) {
+          const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), ATB_TILE, 1024);
+          const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), ATB_TILE, 1024);
+          mbar_wait(bar_p, it & 1);  // P / dS tiles written, S / dP consumed
           tc_fence_after();
-          issue_mma1(kb + 1, 0);
-        }
-        if (qt == 0 && kb > 0) {
-          mbar_wait(bar_kvfree, (kb - 1) & 1);  // the previous key block's dK / dV have left TMEM
+          // the next (key block, query tile)'s scores go first so its softmax math overlaps this MMA 2
+          if (qt + 1 < nt) {
+            if (kb == 0) mbar_wait(&bar_ld[1], ph);
+            tc_fence_after();
+            issue_mma1(kb, qt + 1);
+          } else if (kb + 1 < nt) {
+            mbar_wait(&bar_ld[2], ph);
+            tc_fence_after();
+            issue_mma1(kb + 1, 0);
+          }
+          if (qt == 0 && kvn > 0) mbar_wait(bar_kvfree, (kvn - 1) & 1);  // previous dK / dV have left TMEM
+          if (kb == 0 && qt == 0 && n > 0) mbar_wait(bar_dqfree, (n - 1) & 1);  // previous item's dQ likewise
           tc_fence_after();
-        }
-        // MMA 2: contraction over the 128 queries (dV, dK) and over the block's keys (dQ)
-        const uint64_t dP_mn = make_smem_desc_sw128(smem_u32(sP), ATB_TILE, 1024);
-        const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), ATB_TILE, 1024);
+          // MMA 2: contraction over the 128 queries (dV, dK) and over the block's keys (dQ)
+          const uint64_t dP_mn = make_smem_desc_sw128(smem_u32(sP), ATB_TILE, 1024);
+          const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), ATB_TILE, 1024);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem + T_DV, dP_mn + k * 128, dO_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + T_DV, dP_mn + k * 128, dO_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem + T_DK, dS_mn + k * 128, dQ_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
-        const int ks = kwb >> 4;
-        for (int k = 0; k < ks; ++k) {
-          const uint64_t dS_k = make_smem_desc_sw128(smem_u32(sdS + (k >> 2) * ATB_TILE) + (k & 3) * 32, 16, 1024);
-          umma_bf16(tmem + T_DQ + qt * 64, dS_k, dK_mn + k * 128, id_dq, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + T_DK, dS_mn + k * 128, dQ_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+          const int ks = kwb >> 4;
+          for (int k = 0; k < ks; ++k) {
+            const uint64_t dS_k = make_smem_desc_sw128(smem_u32(sdS + (k >> 2) * ATB_TILE) + (k & 3) * 32, 16, 1024);
+            umma_bf16(tmem + T_DQ + qt * 64, dS_k, dK_mn + k * 128, id_dq, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_m2);
+          // operand tiles whose last reader was just issued: free them for the next item's loads
+          if (kb == 0 && qt == nt - 1) umma_commit(&bar_free[0]);
+          if (kb == nt - 1 && qt == 0) umma_commit(&bar_free[1]);
+          if (nt > 1 && kb == 1 && qt == nt - 1) umma_commit(&bar_free[2]);
+          if (nt > 1 && kb == nt - 1 && qt == 1) umma_commit(&bar_free[3]);
+          if (kb == nt - 1 && qt == nt - 1 && has_next) {
+            // first scores of the next item (its Q0 / dO0 / K0 / V0 were prefetched)
+            mbar_wait(&bar_ld[0], ph ^ 1);
+            tc_fence_after();
+            issue_mma1(0, 0);
+          }
         }
-        umma_commit(bar_m2);
       }
     }
   } else if (warp < 8) {
@@ -420,147 +461,154 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const int r = quarter * 32 + lane;  // row inside the 128-row tile (TMEM lane)
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sl2 = p.scale * ATC_LOG2E;
-    const float* lse_bh = p.lse + (static_cast<long long>(b) * p.H + h) * p.N;
     uint8_t* stg = sP + warp * 4096;  // output staging (sP is idle whenever it is used)
     const long long rs = 3LL * hd;
-    __nv_bfloat16* g_bh = p.dqkv + static_cast<long long>(b) * p.N * rs + h * 64;
+    int it = 0;
+    int n = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
+      const int b = item / p.H, h = item % p.H;
+      const float* lse_bh = p.lse + (static_cast<long long>(b) * p.H + h) * p.N;
+      __nv_bfloat16* g_bh = p.dqkv + static_cast<long long>(b) * p.N * rs + h * 64;
+      float* delta = sDelta + (n & 1) * 256;
 
-    // store this warp's 32 rows x 64 bf16 (TMEM columns [col, col+64) scaled by 1) to dqkv slot `slot`
-    auto store_rows = [&](uint32_t col, int slot, int row0) {
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(lane_base + col, o0);
-      tmem_ld_32x32(lane_base + col + 32, o1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t* src = u < 4 ? &o0[u * 8] : &o1[(u - 4) * 8];
-        uint4 w;
-        w.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
-        w.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
-        w.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
-        w.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
-        *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3);
-        const int unit = (lane & 7) ^ (rr & 7);
-        const int tok = row0 + quarter * 32 + rr;
-        if (tok < p.N)
-          *reinterpret_cast<uint4*>(g_bh + static_cast<long long>(tok) * rs + slot * hd + unit * 8) =
-              *reinterpret_cast<const uint4*>(stg + rr * 128 + ((lane & 7) << 4));
-      }
-      __syncwarp();
-    };
-
-    // delta[q] = sum_d dO[q,d] * O[q,d] for query tile `hf`: each thread reads its row of O and dO
-    // (one 128-byte line each) straight from global memory while the TMA loads are in flight —
-    // O never occupies shared memory. The two LSE values a thread needs live in registers.
-    float lse2[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) lse2[t] = (t * 128 + r < p.N) ? __ldg(lse_bh + t * 128 + r) * ATC_LOG2E : INFINITY;
-    if (hf < nqt) {
-      const int q = hf * 128 + r;
-      float acc = 0.f;
-      if (q < p.N) {
-        const long long off = (static_cast<long long>(b) * p.N + q) * hd + h * 64;
-        const uint4* orow = reinterpret_cast<const uint4*>(p.o + off);
-        const uint4* grow = reinterpret_cast<const uint4*>(p.dout + off);
+      // store this warp's 32 rows x 64 bf16 (TMEM columns [col, col+64)) to dqkv slot `slot`
+      auto store_rows = [&](uint32_t col, int slot, int row0) {
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(lane_base + col, o0);
+        tmem_ld_32x32(lane_base + col + 32, o1);
+        tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const uint4 a = __ldg(orow + u);
-          const uint4 g = __ldg(grow + u);
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 af = unpack_bf16(aw[j]), gf = unpack_bf16(gw[j]);
-            acc = fmaf(af.x, gf.x, acc);
-            acc = fmaf(af.y, gf.y, acc);
-          }
+          const uint32_t* src = u < 4 ? &o0[u * 8] : &o1[(u - 4) * 8];
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
+          w.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
+          w.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
+          w.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
         }
-      }
-      sDelta[hf * 128 + r] = acc;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 math warps only
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3);
+          const int unit = (lane & 7) ^ (rr & 7);
+          const int tok = row0 + quarter * 32 + rr;
+          if (tok < p.N)
+            *reinterpret_cast<uint4*>(g_bh + static_cast<long long>(tok) * rs + slot * hd + unit * 8) =
+                *reinterpret_cast<const uint4*>(stg + rr * 128 + ((lane & 7) << 4));
+        }
+        __syncwarp();
+      };
 
-    int it = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      for (int qt = 0; qt < nqt; ++qt, ++it) {
-        const float l2 = lse2[qt];
-        const float dl = sDelta[qt * 128 + r];
-        mbar_wait(bar_s, it & 1);
-        tc_fence_after();
-        uint32_t pk[2][16], dk[2][16];
-        const bool rows_live = qt * 128 + quarter * 32 < p.N;  // warp-uniform
+      // delta[q] = sum_d dO[q,d] * O[q,d] for query tile `hf`: each thread reads its row of O and dO
+      // (one 128-byte line each) straight from global memory — O never occupies shared memory.
+      // The two LSE values a thread needs live in registers.
+      float lse2[2];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int key0 = kb * 128 + hf * 64 + c * 32;
-          if (!rows_live || key0 >= p.N) {  // nothing but padding here: P = dS = 0, no TMEM traffic
+      for (int t = 0; t < 2; ++t) lse2[t] = (t * 128 + r < p.N) ? __ldg(lse_bh + t * 128 + r) * ATC_LOG2E : INFINITY;
+      if (hf < nt) {
+        const int q = hf * 128 + r;
+        float acc = 0.f;
+        if (q < p.N) {
+          const long long off = (static_cast<long long>(b) * p.N + q) * hd + h * 64;
+          const uint4* orow = reinterpret_cast<const uint4*>(p.o + off);
+          const uint4* grow = reinterpret_cast<const uint4*>(p.dout + off);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { pk[c][i] = 0u; dk[c][i] = 0u; }
-            continue;
-          }
-          uint32_t s[32], d[32];
-          tmem_ld_32x32(lane_base + T_S + hf * 64 + c * 32, s);
-          tmem_ld_32x32(lane_base + T_DP + hf * 64 + c * 32, d);
-          tmem_ld_wait();
-          if (key0 + 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
-            const float dls = dl * p.scale;
+          for (int u = 0; u < 8; ++u) {
+            const uint4 a = __ldg(orow + u);
+            const uint4 g = __ldg(grow + u);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
-              const float p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
-              const float s0 = p0 * fmaf(__uint_as_float(d[i]), p.scale, -dls);
-              const float s1 = p1 * fmaf(__uint_as_float(d[i + 1]), p.scale, -dls);
-              pk[c][i >> 1] = pack_bf16(p0, p1);
-              dk[c][i >> 1] = pack_bf16(s0, s1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float p0 = 0.f, p1 = 0.f, s0 = 0.f, s1 = 0.f;
-              if (key0 + i < p.N) {
-                p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
-                s0 = p0 * (__uint_as_float(d[i]) - dl) * p.scale;
-              }
-              if (key0 + i + 1 < p.N) {
-                p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
-                s1 = p1 * (__uint_as_float(d[i + 1]) - dl) * p.scale;
-              }
-              pk[c][i >> 1] = pack_bf16(p0, p1);
-              dk[c][i >> 1] = pack_bf16(s0, s1);
+            for (int j = 0; j < 4; ++j) {
+              const float2 af = unpack_bf16(aw[j]), gf = unpack_bf16(gw[j]);
+              acc = fmaf(af.x, gf.x, acc);
+              acc = fmaf(af.y, gf.y, acc);
             }
           }
         }
-        if (it > 0) mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 no longer reads sP / sdS
-        uint8_t* prow = sP + hf * ATB_TILE + r * 128;
-        uint8_t* srow = sdS + hf * ATB_TILE + r * 128;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int unit = (c * 4 + u) ^ (r & 7);
-            *reinterpret_cast<uint4*>(prow + (unit << 4)) =
-                make_uint4(pk[c][u * 4], pk[c][u * 4 + 1], pk[c][u * 4 + 2], pk[c][u * 4 + 3]);
-            *reinterpret_cast<uint4*>(srow + (unit << 4)) =
-                make_uint4(dk[c][u * 4], dk[c][u * 4 + 1], dk[c][u * 4 + 2], dk[c][u * 4 + 3]);
-          }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
-        tc_fence_before();
-        mbar_arrive(bar_p);
+        delta[hf * 128 + r] = acc;
       }
-      // key block done: dK (warps 0-3) and dV (warps 4-7) leave TMEM
-      mbar_wait(bar_m2, (it - 1) & 1);
-      tc_fence_after();
-      store_rows(hf == 0 ? T_DK : T_DV, hf == 0 ? 1 : 2, kb * 128);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 math warps only
+
+      for (int kb = 0; kb < nt; ++kb) {
+        for (int qt = 0; qt < nt; ++qt, ++it) {
+          const float l2 = lse2[qt];
+          const float dl = delta[qt * 128 + r];
+          mbar_wait(bar_s, it & 1);
+          tc_fence_after();
+          uint32_t pk[2][16], dk[2][16];
+          const bool rows_live = qt * 128 + quarter * 32 < p.N;  // warp-uniform
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int key0 = kb * 128 + hf * 64 + c * 32;
+            if (!rows_live || key0 >= p.N) {  // nothing but padding here: P = dS = 0, no TMEM traffic
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { pk[c][i] = 0u; dk[c][i] = 0u; }
+              continue;
+            }
+            uint32_t s[32], d[32];
+            tmem_ld_32x32(lane_base + T_S + hf * 64 + c * 32, s);
+            tmem_ld_32x32(lane_base + T_DP + hf * 64 + c * 32, d);
+            tmem_ld_wait();
+            if (key0 + 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
+              const float dls = dl * p.scale;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
+                const float p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
+                const float s0 = p0 * fmaf(__uint_as_float(d[i]), p.scale, -dls);
+                const float s1 = p1 * fmaf(__uint_as_float(d[i + 1]), p.scale, -dls);
+                pk[c][i >> 1] = pack_bf16(p0, p1);
+                dk[c][i >> 1] = pack_bf16(s0, s1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                float p0 = 0.f, p1 = 0.f, s0 = 0.f, s1 = 0.f;
+                if (key0 + i < p.N) {
+                  p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
+                  s0 = p0 * (__uint_as_float(d[i]) - dl) * p.scale;
+                }
+                if (key0 + i + 1 < p.N) {
+                  p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
+                  s1 = p1 * (__uint_as_float(d[i + 1]) - dl) * p.scale;
+                }
+                pk[c][i >> 1] = pack_bf16(p0, p1);
+                dk[c][i >> 1] = pack_bf16(s0, s1);
+              }
+            }
+          }
+          if (it > 0) mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 no longer reads sP / sdS
+          uint8_t* prow = sP + hf * ATB_TILE + r * 128;
+          uint8_t* srow = sdS + hf * ATB_TILE + r * 128;
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int unit = (c * 4 + u) ^ (r & 7);
+              *reinterpret_cast<uint4*>(prow + (unit << 4)) =
+                  make_uint4(pk[c][u * 4], pk[c][u * 4 + 1], pk[c][u * 4 + 2], pk[c][u * 4 + 3]);
+              *reinterpret_cast<uint4*>(srow + (unit << 4)) =
+                  make_uint4(dk[c][u * 4], dk[c][u * 4 + 1], dk[c][u * 4 + 2], dk[c][u * 4 + 3]);
+            }
+          fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+          tc_fence_before();
+          mbar_arrive(bar_p);
+        }
+        // key block done: dK (warps 0-3) and dV (warps 4-7) leave TMEM
+        mbar_wait(bar_m2, (it - 1) & 1);
+        tc_fence_after();
+        store_rows(hf == 0 ? T_DK : T_DV, hf == 0 ? 1 : 2, kb * 128);
+        tc_fence_before();
+        mbar_arrive(bar_kvfree);
+      }
+      // all key blocks done: dQ of query tile `hf`
+      if (hf < nt) {
+        tc_fence_after();
+        store_rows(T_DQ + hf * 64, 0, hf * 128);
+      }
       tc_fence_before();
-      mbar_arrive(bar_kvfree);
-    }
-    // all key blocks done: dQ of query tile `hf`
-    if (hf < nqt) {
-      tc_fence_after();
-      store_rows(T_DQ + hf * 64, 0, hf * 128);
+      mbar_arrive(bar_dqfree);
     }
   }
   tc_fence_before();
@@ -581,6 +629,7 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
   p.N = static_cast<int>(tokens);
   p.H = static_cast<int>(heads);
   p.kw = static_cast<int>((tokens + 15) / 16 * 16);
+  p.items = static_cast<int>(batch * heads);
   p.scale = scale;
   p.lse = lse;
   p.o = reinterpret_cast<const __nv_bfloat16*>(out);
@@ -596,7 +645,8 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
     FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM));
     configured = true;
   }
-  FV_CHECK_CUDA(fv::launch_pdl(attn_tc_bwd_kernel, dim3(static_cast<unsigned>(batch * heads)), dim3(ATB_THREADS), ATB_SMEM, stream, mq, mdo, p));
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  FV_CHECK_CUDA(fv::launch_pdl(attn_tc_bwd_kernel, dim3(static_cast<unsigned>(grid)), dim3(ATB_THREADS), ATB_SMEM, stream, mq, mdo, p));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
