@@ -278,9 +278,9 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
 //   separate pass over HBM).
 // Q / dO tiles double as A operands (K-major) and B operands (MN-major); K / V likewise — every
 // tile is loaded once per (batch, head) and nothing is transposed or re-materialised.
-constexpr int ATB_THREADS = 320;  // warps 0-7 math, warp 8 MMA issue, warp 9 TMEM alloc + TMA producer
+constexpr int ATB_THREADS = 384;  // warps 0-7 math, 8 MMA issue, 9 TMEM alloc + TMA producer, 10-11 delta / LSE helpers
 constexpr int ATB_TILE = 128 * 128;  // bytes of one [128 x 64] bf16 tile
-constexpr int ATB_SMEM = 12 * ATB_TILE + 1024 + 2048 + 256;  // Q(2) dO(2) K(2) V(2) P(2) dS(2) + delta[2][256] + barriers
+constexpr int ATB_SMEM = 12 * ATB_TILE + 1024 + 4096 + 256;  // Q(2) dO(2) K(2) V(2) P(2) dS(2) + {lse, delta}[2 items][256] + barriers
 
 struct AttnBwdParams {
   int N, H, kw;
@@ -312,8 +312,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint8_t* sV = sK + 2 * ATB_TILE;     // 2 tiles
   uint8_t* sP = sV + 2 * ATB_TILE;     // 2 column blocks of 64 keys
   uint8_t* sdS = sP + 2 * ATB_TILE;    // 2 column blocks
-  float* sDelta = reinterpret_cast<float*>(sdS + 2 * ATB_TILE);  // [2 items][256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 512);
+  float* sAux = reinterpret_cast<float*>(sdS + 2 * ATB_TILE);  // [2 items][lse*log2e[256], delta[256]]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAux + 1024);
   uint64_t* bar_ld = bars + 0;     // [3] loaded: {Q0 dO0 K0 V0}, {Q1 dO1}, {K1 V1}
   uint64_t* bar_free = bars + 3;   // [4] last reader retired: {K0 V0}, {Q0 dO0}, {K1 V1}, {Q1 dO1}
   uint64_t* bar_s = bars + 7;
@@ -321,7 +321,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint64_t* bar_m2 = bars + 9;
   uint64_t* bar_kvfree = bars + 10;
   uint64_t* bar_dqfree = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_aux = bars + 12;   // [2] lse / delta of item n ready in sAux[n & 1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.N + 127) >> 7;  // query tiles == key blocks (1 or 2)
@@ -338,6 +339,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     mbar_init(bar_m2, 1);
     mbar_init(bar_kvfree, 256);
     mbar_init(bar_dqfree, 256);
+    mbar_init(&bar_aux[0], 64);
+    mbar_init(&bar_aux[1], 64);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -455,61 +458,23 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         }
       }
     }
-  } else if (warp < 8) {
-    // ------------------------------ math + output warps ----------------------------------------
-    const int quarter = warp & 3, hf = warp >> 2;
-    const int r = quarter * 32 + lane;  // row inside the 128-row tile (TMEM lane)
-    const uint32_t lane_base = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-    const float sl2 = p.scale * ATC_LOG2E;
-    uint8_t* stg = sP + warp * 4096;  // output staging (sP is idle whenever it is used)
-    const long long rs = 3LL * hd;
-    int it = 0;
+  } else if (warp >= 10) {
+    // ------------------------------ delta / LSE helpers ------------------------------------------
+    // delta[q] = sum_d dO[q,d] * O[q,d] and lse[q] * log2(e) of the NEXT items, one row per thread
+    // pass straight from global memory (O never occupies shared memory), one item ahead of the math
+    // warps — those found the three dependent global round trips at every item start on their
+    // critical path (ncu: 22 % of their samples).
+    const int t = threadIdx.x - 320;
     int n = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
       const int b = item / p.H, h = item % p.H;
+      if (n >= 2) mbar_wait(bar_dqfree, n & 1);  // item n-2 fully retired: its buffer may be rewritten
+      float* aux = sAux + (n & 1) * 512;
       const float* lse_bh = p.lse + (static_cast<long long>(b) * p.H + h) * p.N;
-      __nv_bfloat16* g_bh = p.dqkv + static_cast<long long>(b) * p.N * rs + h * 64;
-      float* delta = sDelta + (n & 1) * 256;
-
-      // store this warp's 32 rows x 64 bf16 (TMEM columns [col, col+64)) to dqkv slot `slot`
-      auto store_rows = [&](uint32_t col, int slot, int row0) {
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32(lane_base + col, o0);
-        tmem_ld_32x32(lane_base + col + 32, o1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t* src = u < 4 ? &o0[u * 8] : &o1[(u - 4) * 8];
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(src[0]), __uint_as_float(src[1]));
-          w.y = pack_bf16(__uint_as_float(src[2]), __uint_as_float(src[3]));
-          w.z = pack_bf16(__uint_as_float(src[4]), __uint_as_float(src[5]));
-          w.w = pack_bf16(__uint_as_float(src[6]), __uint_as_float(src[7]));
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + (lane >> 3);
-          const int unit = (lane & 7) ^ (rr & 7);
-          const int tok = row0 + quarter * 32 + rr;
-          if (tok < p.N)
-            *reinterpret_cast<uint4*>(g_bh + static_cast<long long>(tok) * rs + slot * hd + unit * 8) =
-                *reinterpret_cast<const uint4*>(stg + rr * 128 + ((lane & 7) << 4));
-        }
-        __syncwarp();
-      };
-
-      // delta[q] = sum_d dO[q,d] * O[q,d] for query tile `hf`: each thread reads its row of O and dO
-      // (one 128-byte line each) straight from global memory — O never occupies shared memory.
-      // The two LSE values a thread needs live in registers.
-      float lse2[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) lse2[t] = (t * 128 + r < p.N) ? __ldg(lse_bh + t * 128 + r) * ATC_LOG2E : INFINITY;
-      if (hf < nt) {
-        const int q = hf * 128 + r;
-        float acc = 0.f;
+      for (int q = t; q < nt * 128; q += 64) {
+        float l2 = INFINITY, acc = 0.f;
         if (q < p.N) {
+          l2 = __ldg(lse_bh + q) * ATC_LOG2E;
           const long long off = (static_cast<long long>(b) * p.N + q) * hd + h * 64;
           const uint4* orow = reinterpret_cast<const uint4*>(p.o + off);
           const uint4* grow = reinterpret_cast<const uint4*>(p.dout + off);
@@ -526,14 +491,68 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
             }
           }
         }
-        delta[hf * 128 + r] = acc;
+        aux[q] = l2;
+        aux[256 + q] = acc;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 math warps only
+      mbar_arrive(&bar_aux[n & 1]);
+    }
+  } else if (warp < 8) {
+    // ------------------------------ math + output warps ----------------------------------------
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int r = quarter * 32 + lane;  // row inside the 128-row tile (TMEM lane)
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float sl2 = p.scale * ATC_LOG2E;
+    const long long rs = 3LL * hd;
 
+    // this thread's row of TMEM columns [col, col+64) -> 64 bf16 = one 128-byte line of dqkv slot
+    // `slot`, written as four 256-bit stores straight from registers
+    auto store_row = [&](uint32_t col, int b, int h, int slot, int tok) {
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(lane_base + col, o0);
+      tmem_ld_32x32(lane_base + col + 32, o1);
+      tmem_ld_wait();
+      if (tok < p.N) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          w[i] = pack_bf16(__uint_as_float(o0[2 * i]), __uint_as_float(o0[2 * i + 1]));
+          w[16 + i] = pack_bf16(__uint_as_float(o1[2 * i]), __uint_as_float(o1[2 * i + 1]));
+        }
+        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * p.N + tok) * rs + slot * hd + h * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_v8(dst + j * 16, w + j * 8);
+      }
+    };
+    // Drains are deferred by one iteration: dK / dV of a finished key block (and dQ of a finished
+    // item) leave tensor memory AFTER this thread has produced the next iteration's P / dS, so the
+    // wait for their last MMA 2 overlaps useful work instead of idling the math warps (ncu: 13 % of
+    // their samples sat in that wait).
+    bool pend_kv = false, pend_dq = false;
+    int kv_b = 0, kv_h = 0, kv_kb = 0, dq_b = 0, dq_h = 0;
+    auto drain = [&]() {
+      if (pend_kv) {
+        store_row(hf == 0 ? T_DK : T_DV, kv_b, kv_h, hf == 0 ? 1 : 2, kv_kb * 128 + r);
+        tc_fence_before();
+        mbar_arrive(bar_kvfree);
+        pend_kv = false;
+      }
+      if (pend_dq) {
+        if (hf < nt) store_row(T_DQ + hf * 64, dq_b, dq_h, 0, hf * 128 + r);
+        tc_fence_before();
+        mbar_arrive(bar_dqfree);
+        pend_dq = false;
+      }
+    };
+    int it = 0;
+    int n = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
+      const int b = item / p.H, h = item % p.H;
+      const float* aux = sAux + (n & 1) * 512;
+      mbar_wait(&bar_aux[n & 1], (n >> 1) & 1);
       for (int kb = 0; kb < nt; ++kb) {
         for (int qt = 0; qt < nt; ++qt, ++it) {
-          const float l2 = lse2[qt];
-          const float dl = delta[qt * 128 + r];
+          const float l2 = aux[qt * 128 + r];
+          const float dl = aux[256 + qt * 128 + r];
           mbar_wait(bar_s, it & 1);
           tc_fence_after();
           uint32_t pk[2][16], dk[2][16];
@@ -578,7 +597,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
               }
             }
           }
-          if (it > 0) mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 no longer reads sP / sdS
+          if (it > 0) {
+            mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 retired: sP / sdS free, its dK / dV / dQ final
+            tc_fence_after();
+          }
           uint8_t* prow = sP + hf * ATB_TILE + r * 128;
           uint8_t* srow = sdS + hf * ATB_TILE + r * 128;
 #pragma unroll
@@ -594,21 +616,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
           tc_fence_before();
           mbar_arrive(bar_p);
+          drain();  // whatever finished with the previous iteration's MMA 2
+          if (qt == nt - 1) {
+            pend_kv = true;
+            kv_b = b; kv_h = h; kv_kb = kb;
+          }
         }
-        // key block done: dK (warps 0-3) and dV (warps 4-7) leave TMEM
-        mbar_wait(bar_m2, (it - 1) & 1);
-        tc_fence_after();
-        store_rows(hf == 0 ? T_DK : T_DV, hf == 0 ? 1 : 2, kb * 128);
-        tc_fence_before();
-        mbar_arrive(bar_kvfree);
       }
-      // all key blocks done: dQ of query tile `hf`
-      if (hf < nt) {
-        tc_fence_after();
-        store_rows(T_DQ + hf * 64, 0, hf * 128);
-      }
-      tc_fence_before();
-      mbar_arrive(bar_dqfree);
+      pend_dq = true;
+      dq_b = b; dq_h = h;
+    }
+    if (it > 0) {
+      mbar_wait(bar_m2, (it - 1) & 1);
+      tc_fence_after();
+      drain();
     }
   }
   tc_fence_before();

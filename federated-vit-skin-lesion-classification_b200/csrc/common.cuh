@@ -171,6 +171,17 @@ __device__ __forceinline__ void st_stream(void* p, const uint4& v) {
                : "memory");
 }
 
+// 256-bit per-thread global accesses (one whole 32-byte sector each)
+__device__ __forceinline__ void ld_v8(uint32_t (&r)[8], const void* ptr) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
+__device__ __forceinline__ void st_v8(void* ptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 // ---------------------------------------------------------------------------------------------
 // mbarrier / TMA / tcgen05 PTX wrappers
 // ---------------------------------------------------------------------------------------------

@@ -461,16 +461,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
 // reads keep ~3/4 of the shared-memory bandwidth busy at full rate, so the staged transpose (write
 // + read of every output byte through smem) competes with the tensor core; this path does not
 // touch shared memory at all.
-__device__ __forceinline__ void ld_v8(uint32_t (&r)[8], const void* ptr) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(ptr));
-}
-__device__ __forceinline__ void st_v8(void* ptr, const uint32_t* r) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
 // store 32 columns (already packed: 16 words bf16 / 32 words fp32) of one row, clipped at N (N % 8 == 0)
 template <bool BF16>
 __device__ __forceinline__ void store_chunk(void* base, long long ld, long long row, int col0, int N,
