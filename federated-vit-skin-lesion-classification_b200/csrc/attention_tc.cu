@@ -280,7 +280,8 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
 // tile is loaded once per (batch, head) and nothing is transposed or re-materialised.
 constexpr int ATB_THREADS = 384;  // warps 0-7 math, 8 MMA issue, 9 TMEM alloc + TMA producer, 10-11 delta / LSE helpers
 constexpr int ATB_TILE = 128 * 128;  // bytes of one [128 x 64] bf16 tile
-constexpr int ATB_SMEM = 12 * ATB_TILE + 1024 + 4096 + 256;  // Q(2) dO(2) K(2) V(2) P(2) dS(2) + {lse, delta}[2 items][256] + barriers
+constexpr int ATB_AUX = 4;  // items of lse / delta the helper warps may run ahead
+constexpr int ATB_SMEM = 12 * ATB_TILE + 1024 + ATB_AUX * 2048 + 256;  // Q(2) dO(2) K(2) V(2) P(2) dS(2) + {lse, delta}[ATB_AUX][256] + barriers
 
 struct AttnBwdParams {
   int N, H, kw;
@@ -312,8 +313,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint8_t* sV = sK + 2 * ATB_TILE;     // 2 tiles
   uint8_t* sP = sV + 2 * ATB_TILE;     // 2 column blocks of 64 keys
   uint8_t* sdS = sP + 2 * ATB_TILE;    // 2 column blocks
-  float* sAux = reinterpret_cast<float*>(sdS + 2 * ATB_TILE);  // [2 items][lse*log2e[256], delta[256]]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sAux + 1024);
+  float* sAux = reinterpret_cast<float*>(sdS + 2 * ATB_TILE);  // [ATB_AUX items][lse*log2e[256], delta[256]]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAux + ATB_AUX * 512);
   uint64_t* bar_ld = bars + 0;     // [3] loaded: {Q0 dO0 K0 V0}, {Q1 dO1}, {K1 V1}
   uint64_t* bar_free = bars + 3;   // [4] last reader retired: {K0 V0}, {Q0 dO0}, {K1 V1}, {Q1 dO1}
   uint64_t* bar_s = bars + 7;
@@ -321,8 +322,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint64_t* bar_m2 = bars + 9;
   uint64_t* bar_kvfree = bars + 10;
   uint64_t* bar_dqfree = bars + 11;
-  uint64_t* bar_aux = bars + 12;   // [2] lse / delta of item n ready in sAux[n & 1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bar_aux = bars + 12;                // [ATB_AUX] lse / delta of item n ready in sAux[n % ATB_AUX]
+  uint64_t* bar_auxfree = bar_aux + ATB_AUX;    // [ATB_AUX] ... and read for the last time
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_auxfree + ATB_AUX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.N + 127) >> 7;  // query tiles == key blocks (1 or 2)
@@ -339,8 +341,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     mbar_init(bar_m2, 1);
     mbar_init(bar_kvfree, 256);
     mbar_init(bar_dqfree, 256);
-    mbar_init(&bar_aux[0], 64);
-    mbar_init(&bar_aux[1], 64);
+    for (int i = 0; i < ATB_AUX; ++i) {
+      mbar_init(&bar_aux[i], 64);
+      mbar_init(&bar_auxfree[i], 256);
+    }
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -462,39 +466,60 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     // ------------------------------ delta / LSE helpers ------------------------------------------
     // delta[q] = sum_d dO[q,d] * O[q,d] and lse[q] * log2(e) of the NEXT items, one row per thread
     // pass straight from global memory (O never occupies shared memory), one item ahead of the math
-    // warps — those found the three dependent global round trips at every item start on their
-    // critical path (ncu: 22 % of their samples).
+    // warps (up to ATB_AUX - 1 items) — those found the three dependent global round trips at every
+    // item start on their critical path (ncu: 22 % of their samples).
     const int t = threadIdx.x - 320;
     int n = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
       const int b = item / p.H, h = item % p.H;
-      if (n >= 2) mbar_wait(bar_dqfree, n & 1);  // item n-2 fully retired: its buffer may be rewritten
-      float* aux = sAux + (n & 1) * 512;
+      const int slot = n % ATB_AUX;
+      if (n >= ATB_AUX) mbar_wait(&bar_auxfree[slot], (n / ATB_AUX - 1) & 1);  // previous tenant read out
+      float* aux = sAux + slot * 512;
       const float* lse_bh = p.lse + (static_cast<long long>(b) * p.H + h) * p.N;
-      for (int q = t; q < nt * 128; q += 64) {
-        float l2 = INFINITY, acc = 0.f;
-        if (q < p.N) {
-          l2 = __ldg(lse_bh + q) * ATC_LOG2E;
-          const long long off = (static_cast<long long>(b) * p.N + q) * hd + h * 64;
-          const uint4* orow = reinterpret_cast<const uint4*>(p.o + off);
-          const uint4* grow = reinterpret_cast<const uint4*>(p.dout + off);
+      // two rows per pass: 32 independent 128-bit loads in flight per thread
+      for (int q0 = t; q0 < nt * 128; q0 += 128) {
+        uint4 a[2][8], g[2][8];
+        float l2[2] = {INFINITY, INFINITY};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int q = q0 + j * 64;
+          if (q < p.N) {
+            const long long off = (static_cast<long long>(b) * p.N + q) * hd + h * 64;
+            const uint4* orow = reinterpret_cast<const uint4*>(p.o + off);
+            const uint4* grow = reinterpret_cast<const uint4*>(p.dout + off);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              a[j][u] = __ldg(orow + u);
+              g[j][u] = __ldg(grow + u);
+            }
+            l2[j] = __ldg(lse_bh + q) * ATC_LOG2E;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[j][u] = g[j][u] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int q = q0 + j * 64;
+          float acc = 0.f;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const uint4 a = __ldg(orow + u);
-            const uint4 g = __ldg(grow + u);
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+            const uint32_t aw[4] = {a[j][u].x, a[j][u].y, a[j][u].z, a[j][u].w};
+            const uint32_t gw[4] = {g[j][u].x, g[j][u].y, g[j][u].z, g[j][u].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 af = unpack_bf16(aw[j]), gf = unpack_bf16(gw[j]);
+            for (int w = 0; w < 4; ++w) {
+              const float2 af = unpack_bf16(aw[w]), gf = unpack_bf16(gw[w]);
               acc = fmaf(af.x, gf.x, acc);
               acc = fmaf(af.y, gf.y, acc);
             }
           }
+          if (q < nt * 128) {
+            aux[q] = l2[j];
+            aux[256 + q] = acc;
+          }
         }
-        aux[q] = l2;
-        aux[256 + q] = acc;
       }
-      mbar_arrive(&bar_aux[n & 1]);
+      mbar_arrive(&bar_aux[slot]);
     }
   } else if (warp < 8) {
     // ------------------------------ math + output warps ----------------------------------------
@@ -547,8 +572,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     int n = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
       const int b = item / p.H, h = item % p.H;
-      const float* aux = sAux + (n & 1) * 512;
-      mbar_wait(&bar_aux[n & 1], (n >> 1) & 1);
+      const float* aux = sAux + (n % ATB_AUX) * 512;
+      mbar_wait(&bar_aux[n % ATB_AUX], (n / ATB_AUX) & 1);
       for (int kb = 0; kb < nt; ++kb) {
         for (int qt = 0; qt < nt; ++qt, ++it) {
           const float l2 = aux[qt * 128 + r];
@@ -559,15 +584,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           const bool rows_live = qt * 128 + quarter * 32 < p.N;  // warp-uniform
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const int key0 = kb * 128 + hf * 64 + c * 32;
+            // 32-key chunks are dealt out alternately (group 0: chunks 0 and 2, group 1: 1 and 3) so a
+            // short last key block (69 keys at N = 197) still splits evenly between the two groups
+            const int ch = 2 * c + hf;
+            const int key0 = kb * 128 + ch * 32;
             if (!rows_live || key0 >= p.N) {  // nothing but padding here: P = dS = 0, no TMEM traffic
 #pragma unroll
               for (int i = 0; i < 16; ++i) { pk[c][i] = 0u; dk[c][i] = 0u; }
               continue;
             }
             uint32_t s[32], d[32];
-            tmem_ld_32x32(lane_base + T_S + hf * 64 + c * 32, s);
-            tmem_ld_32x32(lane_base + T_DP + hf * 64 + c * 32, d);
+            tmem_ld_32x32(lane_base + T_S + ch * 32, s);
+            tmem_ld_32x32(lane_base + T_DP + ch * 32, d);
             tmem_ld_wait();
             if (key0 + 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
               const float dls = dl * p.scale;
@@ -601,18 +629,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
             mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 retired: sP / sdS free, its dK / dV / dQ final
             tc_fence_after();
           }
-          uint8_t* prow = sP + hf * ATB_TILE + r * 128;
-          uint8_t* srow = sdS + hf * ATB_TILE + r * 128;
+          // chunk ch = 2c + hf: column block ch >> 1 == c (64 keys each), 64-byte half ch & 1 == hf
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 2; ++c) {
+            uint8_t* prow = sP + c * ATB_TILE + r * 128;
+            uint8_t* srow = sdS + c * ATB_TILE + r * 128;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const int unit = (c * 4 + u) ^ (r & 7);
+              const int unit = (hf * 4 + u) ^ (r & 7);
               *reinterpret_cast<uint4*>(prow + (unit << 4)) =
                   make_uint4(pk[c][u * 4], pk[c][u * 4 + 1], pk[c][u * 4 + 2], pk[c][u * 4 + 3]);
               *reinterpret_cast<uint4*>(srow + (unit << 4)) =
                   make_uint4(dk[c][u * 4], dk[c][u * 4 + 1], dk[c][u * 4 + 2], dk[c][u * 4 + 3]);
             }
+          }
           fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
           tc_fence_before();
           mbar_arrive(bar_p);
@@ -623,6 +653,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           }
         }
       }
+      mbar_arrive(&bar_auxfree[n % ATB_AUX]);
       pend_dq = true;
       dq_b = b; dq_h = h;
     }
