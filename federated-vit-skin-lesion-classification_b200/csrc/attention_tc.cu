@@ -81,13 +81,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem = *tmem_slot;
   pdl_wait();  // nothing above touches memory another kernel produced
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 4) {
+    // the whole warp walks the loop, one elected lane issues: warp-uniform control flow keeps the
+    // descriptors in uniform registers and every TMA / tcgen05.mma a single predicated instruction
     const int hd = p.H * 64;
-    mbar_expect_tx(bar_qk, (nqt * ATC_Q + p.kv_box) * 128);
-    for (int t = 0; t < nqt; ++t) tma_load_3d(sQ + t * ATC_Q * 128, &tmap_q, bar_qk, h * 64, t * ATC_Q, b);
-    tma_load_3d(sK, &tmap_kv, bar_qk, hd + h * 64, 0, b);
-    mbar_expect_tx(bar_v, p.kv_box * 128);
-    tma_load_3d(sV, &tmap_kv, bar_v, 2 * hd + h * 64, 0, b);
+    if (elect_one()) {
+      mbar_expect_tx(bar_qk, (nqt * ATC_Q + p.kv_box) * 128);
+      for (int t = 0; t < nqt; ++t) tma_load_3d(sQ + t * ATC_Q * 128, &tmap_q, bar_qk, h * 64, t * ATC_Q, b);
+      tma_load_3d(sK, &tmap_kv, bar_qk, hd + h * 64, 0, b);
+      mbar_expect_tx(bar_v, p.kv_box * 128);
+      tma_load_3d(sV, &tmap_kv, bar_v, 2 * hd + h * 64, 0, b);
+    }
+    __syncwarp();
 
     mbar_wait(bar_qk, 0);
     const uint32_t idesc_s = make_idesc(kFmtBF16, 0, 0, ATC_Q, p.kw);
@@ -101,16 +106,22 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc_fence_after();
       // S = Q K^T : both operands K-major (head dim contiguous), 4 steps of K = 16
       const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + t * ATC_Q * 128), 16, 1024);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(bar_s);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
       mbar_wait(bar_p, ph);
       if (t == 0) mbar_wait(bar_v, 0);
       tc_fence_after();
       // O = P V : A = P from TMEM (16 keys = 8 packed columns per step), B = V MN-major
-      for (int k = 0; k < ksteps; ++k)
-        umma_bf16_ts(tmem + 128, tmem + k * 8, dv + k * (2048 >> 4), idesc_o, k > 0 ? 1u : 0u);
-      umma_commit(bar_o);
+      if (elect_one()) {
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ts(tmem + 128, tmem + k * 8, dv + k * (2048 >> 4), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(bar_o);
+      }
+      __syncwarp();
     }
   } else if (warp < 4) {
     const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
@@ -355,8 +366,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   pdl_wait();  // nothing above touches memory another kernel produced
   constexpr uint32_t T_S = 0, T_DP = 128, T_DK = 256, T_DV = 320, T_DQ = 384;
 
-  if (warp == 9 && lane == 0) {
-    // ------------------------------ TMA producer ----------------------------------------------
+  if (warp == 9) {
+    // ------------------------------ TMA producer (whole warp, elected lane issues) ----------------
     int n = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
       const int b = item / p.H, h = item % p.H;
@@ -364,25 +375,41 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       // a barrier is re-armed only after its previous phase is known complete: the tiles' last
       // readers of item n-1 have retired, so their loads (that phase) finished long ago
       if (n > 0) mbar_wait(&bar_free[0], prev);
-      mbar_expect_tx(&bar_ld[0], 4 * ATB_TILE);
-      tma_load_3d(sK, &tmap_qkv, &bar_ld[0], hd + h * 64, 0, b);
-      tma_load_3d(sV, &tmap_qkv, &bar_ld[0], 2 * hd + h * 64, 0, b);
+      if (elect_one()) {
+        mbar_expect_tx(&bar_ld[0], 4 * ATB_TILE);
+        tma_load_3d(sK, &tmap_qkv, &bar_ld[0], hd + h * 64, 0, b);
+        tma_load_3d(sV, &tmap_qkv, &bar_ld[0], 2 * hd + h * 64, 0, b);
+      }
+      __syncwarp();
       if (n > 0) mbar_wait(&bar_free[1], prev);
-      tma_load_3d(sQ, &tmap_qkv, &bar_ld[0], h * 64, 0, b);
-      tma_load_3d(sdO, &tmap_do, &bar_ld[0], h * 64, 0, b);
+      if (elect_one()) {
+        tma_load_3d(sQ, &tmap_qkv, &bar_ld[0], h * 64, 0, b);
+        tma_load_3d(sdO, &tmap_do, &bar_ld[0], h * 64, 0, b);
+      }
+      __syncwarp();
       if (nt > 1) {
         if (n > 0) mbar_wait(&bar_free[3], prev);
-        mbar_expect_tx(&bar_ld[1], 2 * ATB_TILE);
-        tma_load_3d(sQ + ATB_TILE, &tmap_qkv, &bar_ld[1], h * 64, 128, b);
-        tma_load_3d(sdO + ATB_TILE, &tmap_do, &bar_ld[1], h * 64, 128, b);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_ld[1], 2 * ATB_TILE);
+          tma_load_3d(sQ + ATB_TILE, &tmap_qkv, &bar_ld[1], h * 64, 128, b);
+          tma_load_3d(sdO + ATB_TILE, &tmap_do, &bar_ld[1], h * 64, 128, b);
+        }
+        __syncwarp();
         if (n > 0) mbar_wait(&bar_free[2], prev);
-        mbar_expect_tx(&bar_ld[2], 2 * ATB_TILE);
-        tma_load_3d(sK + ATB_TILE, &tmap_qkv, &bar_ld[2], hd + h * 64, 128, b);
-        tma_load_3d(sV + ATB_TILE, &tmap_qkv, &bar_ld[2], 2 * hd + h * 64, 128, b);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_ld[2], 2 * ATB_TILE);
+          tma_load_3d(sK + ATB_TILE, &tmap_qkv, &bar_ld[2], hd + h * 64, 128, b);
+          tma_load_3d(sV + ATB_TILE, &tmap_qkv, &bar_ld[2], 2 * hd + h * 64, 128, b);
+        }
+        __syncwarp();
       }
     }
-  } else if (warp == 8 && lane == 0) {
-    // ------------------------------ MMA issue --------------------------------------------------
+  } else if (warp == 8) {
+    // ------------------------------ MMA issue (whole warp, elected lane issues) -----------------
+    // Warp-uniform control flow keeps every descriptor in uniform registers and each tcgen05.mma a
+    // single predicated instruction. Issued from inside an `if (lane == 0)` region the compiler
+    // wraps every MMA in a vote + broadcast loop of ~25 dependent instructions — longer than these
+    // N = 64 MMAs take to execute, so the issuing thread, not the tensor pipe, set the pace.
     const uint32_t id_dvk = make_idesc(kFmtBF16, 1, 1, 128, 64);  // A MN-major (P^T / dS^T), B MN-major
     const uint32_t id_dq = make_idesc(kFmtBF16, 0, 1, 128, 64);   // A K-major (dS), B MN-major (K)
     // MMA 1 of (key block, query tile): scores and dP; contraction over the 64 head dims
@@ -394,11 +421,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sV + kb * ATB_TILE), 16, 1024);
       const uint64_t dQ_k = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), 16, 1024);
       const uint64_t dO_k = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), 16, 1024);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_S, dQ_k + k * 2, dK_k + k * 2, id_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_S, dQ_k + k * 2, dK_k + k * 2, id_s, k > 0 ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_DP, dO_k + k * 2, dV_k + k * 2, id_s, k > 0 ? 1u : 0u);
-      umma_commit(bar_s);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_DP, dO_k + k * 2, dV_k + k * 2, id_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
     };
     int it = 0;   // (key block, query tile) iterations so far, over all items
     int kvn = 0;  // key blocks so far
@@ -436,23 +466,31 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           // MMA 2: contraction over the 128 queries (dV, dK) and over the block's keys (dQ)
           const uint64_t dP_mn = make_smem_desc_sw128(smem_u32(sP), ATB_TILE, 1024);
           const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), ATB_TILE, 1024);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + T_DV, dP_mn + k * 128, dO_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + T_DK, dS_mn + k * 128, dQ_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+          const uint64_t dS_k0 = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
           const int ks = kwb >> 4;
-          for (int k = 0; k < ks; ++k) {
-            const uint64_t dS_k = make_smem_desc_sw128(smem_u32(sdS + (k >> 2) * ATB_TILE) + (k & 3) * 32, 16, 1024);
-            umma_bf16(tmem + T_DQ + qt * 64, dS_k, dK_mn + k * 128, id_dq, (kb > 0 || k > 0) ? 1u : 0u);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem + T_DV, dP_mn + k * 128, dO_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem + T_DK, dS_mn + k * 128, dQ_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (k < ks) {
+                // dS tile k: column block k >> 2 (one 16 KB tile apart), 32 bytes per K = 16 step inside it
+                const uint64_t dS_k = dS_k0 + (((k >> 2) * ATB_TILE + (k & 3) * 32) >> 4);
+                umma_bf16(tmem + T_DQ + qt * 64, dS_k, dK_mn + k * 128, id_dq, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(bar_m2);
+            // operand tiles whose last reader was just issued: free them for the next item's loads
+            if (kb == 0 && qt == nt - 1) umma_commit(&bar_free[0]);
+            if (kb == nt - 1 && qt == 0) umma_commit(&bar_free[1]);
+            if (nt > 1 && kb == 1 && qt == nt - 1) umma_commit(&bar_free[2]);
+            if (nt > 1 && kb == nt - 1 && qt == 1) umma_commit(&bar_free[3]);
           }
-          umma_commit(bar_m2);
-          // operand tiles whose last reader was just issued: free them for the next item's loads
-          if (kb == 0 && qt == nt - 1) umma_commit(&bar_free[0]);
-          if (kb == nt - 1 && qt == 0) umma_commit(&bar_free[1]);
-          if (nt > 1 && kb == 1 && qt == nt - 1) umma_commit(&bar_free[2]);
-          if (nt > 1 && kb == nt - 1 && qt == 1) umma_commit(&bar_free[3]);
+          __syncwarp();
           if (kb == nt - 1 && qt == nt - 1 && has_next) {
             // first scores of the next item (its Q0 / dO0 / K0 / V0 were prefetched)
             mbar_wait(&bar_ld[0], ph ^ 1);

@@ -435,6 +435,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// no swizzle (layout type 0): 8-row x 16-byte core matrices, `lbo` bytes apart along K and `sbo`
+// bytes apart along M/N
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
 // same with 64-byte swizzle (layout type 4): rows are 64 B, 8-row groups 512 B apart
 __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr, uint32_t lbo_bytes,
                                                         uint32_t sbo_bytes) {

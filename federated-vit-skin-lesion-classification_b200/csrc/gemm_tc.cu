@@ -630,7 +630,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int total_tiles = tiles_mn * p.split_k;
 
-  if (warp == 0 && lane == 0) {
+  // Producer and MMA roles: the WHOLE warp walks the loop and one elected lane issues. With
+  // warp-uniform control flow the descriptors / coordinates live in uniform registers and every
+  // TMA / tcgen05.mma is one predicated instruction; issued from inside an `if (lane == 0)` region
+  // the compiler wraps each of them in a vote + broadcast loop (~25 dependent instructions per MMA
+  // — as long as the MMA itself runs, which made the single issuing thread the mainloop's limiter).
+  if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------------------
     int stage = 0;
     uint32_t phase = 0;
@@ -643,42 +648,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], (EPI == FV_EPI_PATCH && p.im2col)
-                                             ? p.gw * p.ph_per_tile * 64 + BN * 64
-                                             : STAGE_BYTES);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
-        if (EPI == FV_EPI_PATCH && p.im2col) {
-          // one k-block = one pixel row of a patch: 16 fp32 = 64 B (the longest contiguous run an
-          // NCHW image offers a patch), channel kb/16, row kb%16. The box walks (px, -, pw, ph,
-          // image*channel), so the smem rows come out in token order; 64-byte swizzle.
-          const int img = m_blk / p.tiles_per_img;
-          const int ph0 = (m_blk - img * p.tiles_per_img) * p.ph_per_tile;
-          tma_load_5d(sa, &tmap_a, &full_bar[stage], 0, kb & 15, 0, ph0, img * p.chans + (kb >> 4));
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * 16, n_blk * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          continue;
-        }
-        if (p.a_major == FV_MAJOR_K) {
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-        } else {
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage],
+                         (EPI == FV_EPI_PATCH && p.im2col) ? p.gw * p.ph_per_tile * 64 + BN * 64 : STAGE_BYTES);
+          if (EPI == FV_EPI_PATCH && p.im2col) {
+            // one k-block = one pixel row of a patch: 16 fp32 = 64 B (the longest contiguous run an
+            // NCHW image offers a patch), channel kb/16, row kb%16. The box walks (px, -, pw, ph,
+            // image*channel), so the smem rows come out in token order; 64-byte swizzle.
+            const int img = m_blk / p.tiles_per_img;
+            const int ph0 = (m_blk - img * p.tiles_per_img) * p.ph_per_tile;
+            tma_load_5d(sa, &tmap_a, &full_bar[stage], 0, kb & 15, 0, ph0, img * p.chans + (kb >> 4));
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * 16, n_blk * BN);
+          } else {
+            if (p.a_major == FV_MAJOR_K) {
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+            } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j)
-            tma_load_2d(sa + j * (64 * BK * 2), &tmap_a, &full_bar[stage], m_blk * BM + j * 64,
-                        kb * BK);
-        }
-        if (p.b_major == FV_MAJOR_K) {
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
-        } else {
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sa + j * (64 * BK * 2), &tmap_a, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
+            }
+            if (p.b_major == FV_MAJOR_K) {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], n_blk * BN + j * 64,
-                        kb * BK);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+            }
+          }
         }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------------------
     const bool tf32 = (EPI == FV_EPI_PATCH) && p.im2col;
     const uint32_t idesc = make_idesc(tf32 ? kFmtTF32 : kFmtBF16, p.a_major, p.b_major, BM, BN);
@@ -707,21 +711,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t sb = sa + A_STAGE_BYTES;
         const uint64_t da = make_smem_desc_sw128(sa, a_lbo, 1024);
         const uint64_t db = make_smem_desc_sw128(sb, b_lbo, 1024);
-        if (tf32) {  // 64-byte rows hold 16 fp32: two K = 8 steps, 32 bytes apart
-          const uint64_t da64 = make_smem_desc_sw64(sa, 16, 512);
-          const uint64_t db64 = make_smem_desc_sw64(sb, 16, 512);
+        if (elect_one()) {
+          if (tf32) {  // 64-byte rows hold 16 fp32: two K = 8 steps, 32 bytes apart
+            const uint64_t da64 = make_smem_desc_sw64(sa, 16, 512);
+            const uint64_t db64 = make_smem_desc_sw64(sb, 16, 512);
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_tf32(tmem_d, da64 + k * 2, db64 + k * 2, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-        } else {
+            for (int k = 0; k < 2; ++k)
+              umma_tf32(tmem_d, da64 + k * 2, db64 + k * 2, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          } else {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_d, da + k * a_kstep, db + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d, da + k * a_kstep, db + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if ((warp == 2 || warp == 3) && EPI == FV_EPI_ACCUM && p.colsum != nullptr) {
@@ -896,7 +904,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
   const int total_tiles = num_m2 * p.num_n_blocks;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
     int stage = 0;
     uint32_t phase = 0;
@@ -907,22 +915,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int row_b = n_blk * BN + static_cast<int>(rank) * HALF_BN;
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
         uint8_t* sa = smem + stage * STAGE2_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
-        tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, row_a);  // A is K-major on this path
-        if (p.b_major == FV_MAJOR_K) {
-          tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
-        } else {
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, row_a);  // A is K-major on this path
+          if (p.b_major == FV_MAJOR_K) {
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
+          } else {
 #pragma unroll
-          for (int j = 0; j < HALF_BN / 64; ++j)
-            tma_load_2d_pair(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], row_b + j * 64, kb * BK);
+            for (int j = 0; j < HALF_BN / 64; ++j)
+              tma_load_2d_pair(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], row_b + j * 64, kb * BK);
+          }
         }
+        __syncwarp();
         if (++stage == STAGES2) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------- MMA issuer (leader CTA only) ---------------------------
+    // The WHOLE warp walks the loop and one elected lane issues: with warp-uniform control flow the
+    // descriptors live in uniform registers and each tcgen05.mma is a single predicated
+    // instruction. (Issued from inside an `if (lane == 0)` region the compiler wraps every MMA in a
+    // vote / broadcast loop — ~25 dependent instructions per MMA, as long as the MMA itself runs.)
     if (rank == 0) {
       const uint32_t idesc = make_idesc(kFmtBF16, FV_MAJOR_K, p.b_major, 2 * BM, BN);
       const uint32_t b_lbo = p.b_major == FV_MAJOR_K ? 16 : 64 * BK * 2;
@@ -941,13 +956,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
           const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, b_lbo, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_pair(tmem_d, da + k * 2, db + k * b_kstep, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_pair(tmem_d, da + k * 2, db + k * b_kstep, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
+          }
+          __syncwarp();
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[acc]);  // accumulator complete -> both CTAs' epilogues
+        if (elect_one()) umma_commit_pair(&tmem_full[acc]);  // accumulator complete -> both CTAs' epilogues
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
