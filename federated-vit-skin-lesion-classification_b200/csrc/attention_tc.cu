@@ -20,7 +20,7 @@
 
 namespace fv {
 
-constexpr int ATC_THREADS = 192;  // warps 0-3 softmax/epilogue, warp 4 TMA+MMA issue, warp 5 TMEM alloc
+constexpr int ATC_THREADS = 192;  // warps 0-3 softmax/epilogue, warp 4 MMA issue, warp 5 TMEM alloc + TMA producer
 constexpr int ATC_Q = 128;
 constexpr int ATC_KV_MAX = 256;
 constexpr int ATC_SMEM = 2 * ATC_Q * 128 + 2 * ATC_KV_MAX * 128 + 1024 + 128;
@@ -28,6 +28,7 @@ constexpr float ATC_LOG2E = 1.4426950408889634f;
 
 struct AttnTcParams {
   int N, H, kw;  // tokens, heads, keys rounded up to 16
+  int items;     // batch * heads
   int kv_box;    // rows of the K/V TMA box
   float scale;
   __nv_bfloat16* out;
@@ -43,11 +44,16 @@ __device__ __forceinline__ float atc_ex2(float x) {
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                    const AttnTcParams p) {
+  // Persistent: two co-resident CTAs per SM walk (batch, head) items; barriers, tensor memory and
+  // descriptors are set up once. A producer warp refills Q / K as soon as the item's last score
+  // MMA has retired and V after its last PV MMA, so the next item's operands arrive while this
+  // item's softmax runs; O leaves straight from registers (256-bit stores), so the Q tiles are not
+  // needed as staging.
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the address space
-  // known to the compiler: LDS / STS instead of generic LD / ST for every staging access
+  // known to the compiler: LDS / STS instead of generic LD / ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                         // 2 x 16 KiB (both query tiles); reused as output staging
+  uint8_t* sQ = smem;                         // 2 x 16 KiB (both query tiles)
   uint8_t* sK = sQ + 2 * ATC_Q * 128;         // 32 KiB
   uint8_t* sV = sK + ATC_KV_MAX * 128;        // 32 KiB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATC_KV_MAX * 128);
@@ -57,11 +63,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* bar_p = bars + 3;
   uint64_t* bar_o = bars + 4;
   uint64_t* bar_done = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_qkfree = bars + 6;
+  uint64_t* bar_vfree = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y / p.H, h = blockIdx.y % p.H;
   const int nqt = (p.N + ATC_Q - 1) / ATC_Q;  // 1 or 2 query tiles, processed back to back
+  const int hd = p.H * 64;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -72,6 +80,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_init(bar_p, 128);
     mbar_init(bar_o, 1);
     mbar_init(bar_done, 128);
+    mbar_init(bar_qkfree, 1);
+    mbar_init(bar_vfree, 1);
     fence_mbar_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 256);
@@ -81,138 +91,142 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem = *tmem_slot;
   pdl_wait();  // nothing above touches memory another kernel produced
 
-  if (warp == 4) {
-    // the whole warp walks the loop, one elected lane issues: warp-uniform control flow keeps the
-    // descriptors in uniform registers and every TMA / tcgen05.mma a single predicated instruction
-    const int hd = p.H * 64;
-    if (elect_one()) {
-      mbar_expect_tx(bar_qk, (nqt * ATC_Q + p.kv_box) * 128);
-      for (int t = 0; t < nqt; ++t) tma_load_3d(sQ + t * ATC_Q * 128, &tmap_q, bar_qk, h * 64, t * ATC_Q, b);
-      tma_load_3d(sK, &tmap_kv, bar_qk, hd + h * 64, 0, b);
-      mbar_expect_tx(bar_v, p.kv_box * 128);
-      tma_load_3d(sV, &tmap_kv, bar_v, 2 * hd + h * 64, 0, b);
+  if (warp == 5) {
+    // ------------------------------ TMA producer (whole warp, elected lane issues) --------------
+    int n = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      const int b = item / p.H, h = item % p.H;
+      if (n > 0) mbar_wait(bar_qkfree, (n - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_qk, (nqt * ATC_Q + p.kv_box) * 128);
+        for (int t = 0; t < nqt; ++t) tma_load_3d(sQ + t * ATC_Q * 128, &tmap_q, bar_qk, h * 64, t * ATC_Q, b);
+        tma_load_3d(sK, &tmap_kv, bar_qk, hd + h * 64, 0, b);
+      }
+      __syncwarp();
+      if (n > 0) mbar_wait(bar_vfree, (n - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_v, p.kv_box * 128);
+        tma_load_3d(sV, &tmap_kv, bar_v, 2 * hd + h * 64, 0, b);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-
-    mbar_wait(bar_qk, 0);
+  } else if (warp == 4) {
+    // ------------------------------ MMA issue (whole warp, elected lane issues) -----------------
     const uint32_t idesc_s = make_idesc(kFmtBF16, 0, 0, ATC_Q, p.kw);
     const uint32_t idesc_o = make_idesc(kFmtBF16, 0, 1, ATC_Q, 64);
     const uint64_t dk = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
     const uint64_t dv = make_smem_desc_sw128(smem_u32(sV), 64 * 128, 1024);
     const int ksteps = p.kw >> 4;
-    for (int t = 0; t < nqt; ++t) {
-      const uint32_t ph = t & 1;
-      if (t > 0) mbar_wait(bar_done, (t - 1) & 1);  // previous tile's O has been read out of TMEM
-      tc_fence_after();
-      // S = Q K^T : both operands K-major (head dim contiguous), 4 steps of K = 16
-      const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + t * ATC_Q * 128), 16, 1024);
-      if (elect_one()) {
+    int n = 0, gt = 0;  // items, query tiles so far
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      mbar_wait(bar_qk, n & 1);
+      for (int t = 0; t < nqt; ++t, ++gt) {
+        if (gt > 0) mbar_wait(bar_done, (gt - 1) & 1);  // previous tile's O has been read out of TMEM
+        tc_fence_after();
+        // S = Q K^T : both operands K-major (head dim contiguous), 4 steps of K = 16
+        const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + t * ATC_Q * 128), 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_s);
+          if (t == nqt - 1) umma_commit(bar_qkfree);  // Q tiles and K may be refilled when these retire
+        }
+        __syncwarp();
+        mbar_wait(bar_p, gt & 1);
+        if (t == 0) mbar_wait(bar_v, n & 1);
+        tc_fence_after();
+        // O = P V : A = P from TMEM (16 keys = 8 packed columns per step), B = V MN-major
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ts(tmem + 128, tmem + k * 8, dv + k * (2048 >> 4), idesc_o, k > 0 ? 1u : 0u);
+          umma_commit(bar_o);
+          if (t == nqt - 1) umma_commit(bar_vfree);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(bar_p, ph);
-      if (t == 0) mbar_wait(bar_v, 0);
-      tc_fence_after();
-      // O = P V : A = P from TMEM (16 keys = 8 packed columns per step), B = V MN-major
-      if (elect_one()) {
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ts(tmem + 128, tmem + k * 8, dv + k * (2048 >> 4), idesc_o, k > 0 ? 1u : 0u);
-        umma_commit(bar_o);
-      }
-      __syncwarp();
     }
   } else if (warp < 4) {
     const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const float sl2 = p.scale * ATC_LOG2E;
     const int nchunks = (p.kw + 31) >> 5;
-    for (int t = 0; t < nqt; ++t) {
-      const uint32_t ph = t & 1;
-      const int q0 = t * ATC_Q;
-      const int q = q0 + warp * 32 + lane;
-      const bool warp_live = q0 + warp * 32 < p.N;  // warp-uniform
-      float mx = -INFINITY, sum = 0.f;
-      mbar_wait(bar_s, ph);
-      tc_fence_after();
-      if (warp_live) {
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if ((c + 1) * 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
+    int gt = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int b = item / p.H, h = item % p.H;
+      for (int t = 0; t < nqt; ++t, ++gt) {
+        const uint32_t ph = gt & 1;
+        const int q0 = t * ATC_Q;
+        const int q = q0 + warp * 32 + lane;
+        const bool warp_live = q0 + warp * 32 < p.N;  // warp-uniform
+        float mx = -INFINITY, sum = 0.f;
+        mbar_wait(bar_s, ph);
+        tc_fence_after();
+        if (warp_live) {
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            if ((c + 1) * 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          } else {
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < p.N) mx = fmaxf(mx, __uint_as_float(r[i]));
-          }
-        }
-        const float mxs = mx * sl2;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t r[32], pk[16];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if ((c + 1) * 32 <= p.N) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs));
-              const float p1 = atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs));
-              sum += p0 + p1;  // fp32 row sum (the saved LSE is the exact log-sum-exp)
-              pk[i >> 1] = pack_bf16(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = (c * 32 + i < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs)) : 0.f;
-              const float p1 = (c * 32 + i + 1 < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs)) : 0.f;
-              sum += p0 + p1;
-              pk[i >> 1] = pack_bf16(p0, p1);
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < p.N) mx = fmaxf(mx, __uint_as_float(r[i]));
             }
           }
-          tmem_st_32x16(taddr + c * 16, pk);  // columns this thread has already consumed
+          const float mxs = mx * sl2;
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t r[32], pk[16];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            if ((c + 1) * 32 <= p.N) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs));
+                const float p1 = atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs));
+                sum += p0 + p1;  // fp32 row sum (the saved LSE is the exact log-sum-exp)
+                pk[i >> 1] = pack_bf16(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = (c * 32 + i < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs)) : 0.f;
+                const float p1 = (c * 32 + i + 1 < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs)) : 0.f;
+                sum += p0 + p1;
+                pk[i >> 1] = pack_bf16(p0, p1);
+              }
+            }
+            tmem_st_32x16(taddr + c * 16, pk);  // columns this thread has already consumed
+          }
+          tmem_st_wait();
         }
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(bar_p);
+        tc_fence_before();
+        mbar_arrive(bar_p);
 
-      mbar_wait(bar_o, ph);
-      tc_fence_after();
-      uint32_t o0[32], o1[32];
-      if (warp_live) {
-        tmem_ld_32x32(taddr + 128, o0);
-        tmem_ld_32x32(taddr + 160, o1);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      mbar_arrive(bar_done);  // TMEM may be overwritten by the next tile's S
-      if (warp_live) {
-        const float inv = 1.0f / sum;
-        uint8_t* stg = sQ + t * ATC_Q * 128 + warp * (32 * 128);  // 32 rows x 128 B, units XOR-swizzled
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t* src = u < 4 ? &o0[u * 8] : &o1[(u - 4) * 8];
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-          w.y = pack_bf16(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-          w.z = pack_bf16(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-          w.w = pack_bf16(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) = w;
+        mbar_wait(bar_o, ph);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        if (warp_live) {
+          tmem_ld_32x32(taddr + 128, o0);
+          tmem_ld_32x32(taddr + 160, o1);
+          tmem_ld_wait();
         }
-        __syncwarp();
-        __nv_bfloat16* ob = p.out + (static_cast<long long>(b) * p.N * p.H + h) * 64;
+        tc_fence_before();
+        mbar_arrive(bar_done);  // TMEM may be overwritten by the next tile's S
+        if (warp_live && q < p.N) {
+          // this thread's row: 64 bf16 = one 128-byte line of out[b, q, h, :], four 256-bit stores
+          const float inv = 1.0f / sum;
+          uint32_t w[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);
-          const int unit = (lane & 7) ^ (r & 7);
-          const int qq = q0 + warp * 32 + r;
-          if (qq < p.N)
-            *reinterpret_cast<uint4*>(ob + static_cast<long long>(qq) * p.H * 64 + unit * 8) =
-                *reinterpret_cast<const uint4*>(stg + r * 128 + ((lane & 7) << 4));
+          for (int i = 0; i < 16; ++i) {
+            w[i] = pack_bf16(__uint_as_float(o0[2 * i]) * inv, __uint_as_float(o0[2 * i + 1]) * inv);
+            w[16 + i] = pack_bf16(__uint_as_float(o1[2 * i]) * inv, __uint_as_float(o1[2 * i + 1]) * inv);
+          }
+          __nv_bfloat16* dst = p.out + ((static_cast<long long>(b) * p.N + q) * p.H + h) * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st_v8(dst + j * 16, w + j * 8);
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = mx * p.scale + logf(sum);
         }
-        if (q < p.N) p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = mx * p.scale + logf(sum);
       }
     }
   }
@@ -254,6 +268,7 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
   p.H = static_cast<int>(heads);
   p.kw = static_cast<int>((tokens + 15) / 16 * 16);
   p.kv_box = p.kw;
+  p.items = static_cast<int>(batch * heads);
   p.scale = scale;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
@@ -267,7 +282,8 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
     FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
     configured = true;
   }
-  dim3 grid(1, static_cast<unsigned>(batch * heads));
+  const int slots = 2 * num_sms();  // two co-resident CTAs per SM
+  const unsigned grid = static_cast<unsigned>(p.items < slots ? p.items : slots);
   FV_CHECK_CUDA(fv::launch_pdl(attn_tc_fwd_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, mq, mkv, p));
   FV_LAUNCH_CHECK();
   return FV_OK;
