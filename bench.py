@@ -303,6 +303,8 @@ def run_gpu_arm(args) -> None:
     if rank == 0:
         peaks = measured_peaks()
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        tpath = ROOT / "profiles" / "r1_ncu_traffic.json"
+        traffic = json.loads(tpath.read_text()) if tpath.exists() else {}
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -315,11 +317,15 @@ def run_gpu_arm(args) -> None:
                            "every step's loss read back to the host (one step late, pinned scalar)"},
             "gpu_launches": launches,
             "roofline": {
-                "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all epilogues)",
+                "bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM: CTA-pair and single-CTA variants, all epilogues)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "gemm_launches": len(trace), "gemm_share_of_step": gemm_ms / ms_total if ms_total else None,
-                "traffic": None,
+                "traffic": traffic.get("dram_bytes_per_launch"), "traffic_unit": "bytes per launch",
+                "traffic_note": (f"ncu --set full, one launch of {traffic.get('kernel')} at {traffic.get('shape')}: "
+                                 f"{traffic.get('dram_bytes_per_launch')} B DRAM vs {traffic.get('algorithmic_bytes_per_launch')} B "
+                                 f"algorithmic, tensor pipe active {traffic.get('tensor_pipe_active_pct_of_elapsed')} % of elapsed "
+                                 f"({traffic.get('source')})") if traffic else None,
                 "step_tflops": value / args.gpus * TRAIN_GFLOP_PER_IMG / 1e3,
                 "step_frac_of_peak": value / args.gpus * TRAIN_GFLOP_PER_IMG / 1e3 / peak,
             },
