@@ -53,7 +53,8 @@ cls_pos_kernel(const float* __restrict__ cls, const float* __restrict__ pos, flo
 }
 
 // out[c] += sum_r a[r, c].  block = 32 x 8; a warp row covers 64 columns (2 per lane).
-template <bool IN_BF16>
+// VEC2 = false: scalar loads for odd widths / leading dimensions (the 7-class head's bias gradient).
+template <bool IN_BF16, bool VEC2 = true>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ a, long long lda, float* __restrict__ out, long long rows,
               int cols, int rows_per_block) {
@@ -66,7 +67,18 @@ colsum_kernel(const void* __restrict__ a, long long lda, float* __restrict__ out
   float2 s = make_float2(0.f, 0.f);
   if (col < cols) {
     for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
-      if (IN_BF16) {
+      if (!VEC2) {
+        const bool two = col + 1 < cols;
+        if (IN_BF16) {
+          const __nv_bfloat16* row = reinterpret_cast<const __nv_bfloat16*>(a) + r * lda;
+          s.x += __bfloat162float(row[col]);
+          if (two) s.y += __bfloat162float(row[col + 1]);
+        } else {
+          const float* row = reinterpret_cast<const float*>(a) + r * lda;
+          s.x += row[col];
+          if (two) s.y += row[col + 1];
+        }
+      } else if (IN_BF16) {
         const uint32_t u = __ldcs(reinterpret_cast<const uint32_t*>(
             reinterpret_cast<const __nv_bfloat16*>(a) + r * lda + col));
         const float2 f = unpack_bf16(u);
@@ -88,7 +100,7 @@ colsum_kernel(const void* __restrict__ a, long long lda, float* __restrict__ out
       s.y += red[j][threadIdx.x].y;
     }
     atomicAdd(out + col, s.x);
-    atomicAdd(out + col + 1, s.y);
+    if (col + 1 < cols) atomicAdd(out + col + 1, s.y);
   }
 }
 
@@ -167,8 +179,8 @@ extern "C" int fv_cls_pos_rows(const float* cls, const float* pos, float* x, int
 extern "C" int fv_colsum(const void* a, int a_dtype, int64_t lda, float* out, int accumulate,
                          int64_t rows, int64_t cols, void* stream) {
   using namespace fv;
-  FV_CHECK_ARG(a && out && rows >= 0 && cols > 0 && cols % 2 == 0 && lda % 2 == 0 && cols < (1LL << 30),
-               "fv_colsum: bad argument (cols and lda must be even)");
+  FV_CHECK_ARG(a && out && rows >= 0 && cols > 0 && lda >= cols && cols < (1LL << 30), "fv_colsum: bad argument");
+  const bool vec2 = cols % 2 == 0 && lda % 2 == 0 && (reinterpret_cast<uintptr_t>(a) & 7) == 0;
   FV_CHECK_ARG(a_dtype == FV_F32 || a_dtype == FV_BF16, "fv_colsum: bad dtype");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!accumulate) FV_CHECK_CUDA(cudaMemsetAsync(out, 0, cols * sizeof(float), st));
@@ -181,10 +193,14 @@ extern "C" int fv_colsum(const void* a, int a_dtype, int64_t lda, float* out, in
   slices = ceil_div(rows, rows_per);
   dim3 grid(col_blocks, static_cast<unsigned>(slices));
   dim3 block(32, 8);
-  if (a_dtype == FV_BF16)
-    FV_CHECK_CUDA(fv::launch_pdl(colsum_kernel<true>, dim3(grid), dim3(block), 0, st, a, lda, out, rows, (int)cols, (int)rows_per));
+  if (a_dtype == FV_BF16 && vec2)
+    FV_CHECK_CUDA(fv::launch_pdl(colsum_kernel<true, true>, dim3(grid), dim3(block), 0, st, a, lda, out, rows, (int)cols, (int)rows_per));
+  else if (a_dtype == FV_BF16)
+    FV_CHECK_CUDA(fv::launch_pdl(colsum_kernel<true, false>, dim3(grid), dim3(block), 0, st, a, lda, out, rows, (int)cols, (int)rows_per));
+  else if (vec2)
+    FV_CHECK_CUDA(fv::launch_pdl(colsum_kernel<false, true>, dim3(grid), dim3(block), 0, st, a, lda, out, rows, (int)cols, (int)rows_per));
   else
-    FV_CHECK_CUDA(fv::launch_pdl(colsum_kernel<false>, dim3(grid), dim3(block), 0, st, a, lda, out, rows, (int)cols, (int)rows_per));
+    FV_CHECK_CUDA(fv::launch_pdl(colsum_kernel<false, false>, dim3(grid), dim3(block), 0, st, a, lda, out, rows, (int)cols, (int)rows_per));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

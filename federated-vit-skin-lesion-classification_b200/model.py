@@ -8,8 +8,8 @@ the backbone is ``fedvit_b200.vit.VisionTransformer`` (hand-written sm_100a kern
 backward) instead of a timm module running on ATen/cuDNN/cuBLAS.
 
 Scope notes: only the ViT family is on this path — the reference's default
-SwinV2 backbone name raises. The 13-d metadata MLP and the two small head GEMMs stay on stock
-PyTorch ops for now (row f2 of the scope table).
+SwinV2 backbone name raises. The classifier head runs on the libfedvit GEMMs (``head.py``, row f2
+of the scope table); the 13-d metadata MLP (BatchNorm1d) stays on stock PyTorch ops.
 """
 from __future__ import annotations
 
@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import timm_b200 as timm
+from .head import classifier_head
 
 _DEFAULT_BACKBONE = "swinv2_large_window12to24_192to384.ms_in22k_ft_in1k"  # reference model.py:89
 
@@ -116,7 +117,8 @@ class ISICClassifier(nn.Module):
             else:
                 emb = self.metadata_branch(metadata)
             feats = torch.cat([feats, emb.to(feats.dtype)], dim=1)
-        return {"logits": self.classifier(feats)}
+        # the two head GEMMs (+ GELU, dropout) run on the libfedvit kernels too (head.py, scope row f2)
+        return {"logits": classifier_head(feats, self.classifier, self.training)}
 
     # -- freezing / optimiser groups --------------------------------------------------------------
     def freeze_backbone(self) -> None:

@@ -145,6 +145,21 @@ def _to_bf16(t: Tensor) -> Tensor:
     return out
 
 
+def weight_operand(p: nn.Parameter, lp: bool) -> Tensor:
+    """GEMM operand for a weight: the fp32 master (fp32 mode) or its bf16 shadow (the FlatArena's
+    bf16 copy, rewritten by the optimiser sweep, when the parameter lives in one)."""
+    w = p.detach()
+    if w.dim() == 4:
+        w = w.reshape(w.shape[0], -1)
+    if not lp:
+        return w
+    a = getattr(p, "_fv_arena", None)
+    if a is not None and a[0].lp is not None and a[0].owns(p):
+        v = a[0].lp_view(p)
+        return v.reshape(v.shape[0], -1) if v.dim() == 4 else v
+    return _to_bf16(w)
+
+
 class _Saved:
     __slots__ = ("lp", "B", "N", "img", "patches", "blocks", "cls_rows", "meanf", "rstdf")
 
@@ -197,17 +212,7 @@ class VisionTransformer(nn.Module):
         return list(self.parameters())
 
     def _w(self, p: nn.Parameter, lp: bool) -> Tensor:
-        """GEMM operand for a weight: the fp32 master (fp32 mode) or its bf16 shadow."""
-        w = p.detach()
-        if w.dim() == 4:
-            w = w.reshape(w.shape[0], -1)
-        if not lp:
-            return w
-        a = getattr(p, "_fv_arena", None)
-        if a is not None and a[0].lp is not None and a[0].owns(p):
-            v = a[0].lp_view(p)
-            return v.reshape(v.shape[0], -1) if v.dim() == 4 else v
-        return _to_bf16(w)
+        return weight_operand(p, lp)
 
     def forward(self, x: Tensor) -> Tensor:
         if not x.is_cuda:

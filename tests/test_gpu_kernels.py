@@ -45,8 +45,9 @@ def test_gemm_bf16_all_layouts(m, n, k, am, bm):
     assert rel_err(out, _gemm_ref(a, b, am, bm) + bias) < 1e-5  # bf16 inputs are exact in fp32; fp32 accumulate
 
 
-def test_gemm_bf16_epilogues():
-    m, n, k = 777, 520, 200
+@pytest.mark.parametrize("m,n,k", [(777, 520, 200),       # single-CTA kernel, ragged in every dimension
+                                   (19000, 1032, 328)])   # 75 x 5 CTA-pair tiles (cta_group::2 kernel), ragged M / N / K
+def test_gemm_bf16_epilogues(m, n, k):
     g = _gen(1)
     a = torch.randn(m, k, device=DEV, generator=g).bfloat16()
     b = torch.randn(n, k, device=DEV, generator=g).bfloat16()

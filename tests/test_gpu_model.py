@@ -8,6 +8,7 @@ import copy
 import numpy as np
 import pytest
 import torch
+import torch.nn as nn
 
 import fedvit_b200  # noqa: F401
 from conftest import micro_config, rel_err, state_from_golden
@@ -483,3 +484,35 @@ def test_stochastic_depth_matches_oracle_with_shared_masks(amp):
     with torch.no_grad():
         a, b = ours(x.to(DEV))["logits"], ours(x.to(DEV))["logits"]
     assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lp", [False, True])
+@pytest.mark.parametrize("batch,width,classes", [(8, 192, 7), (33, 896, 8)])
+def test_native_classifier_head_matches_torch(lp, batch, width, classes):
+    """head.py (scope row f2): Linear-GELU-Dropout-Linear forward and every gradient on the libfedvit
+    GEMMs against the stock PyTorch modules (reference model.py:139-144,206)."""
+    from fedvit_b200.head import classifier_head
+
+    torch.manual_seed(7)
+    ref = nn.Sequential(nn.Linear(width, 512), nn.GELU(), nn.Dropout(0.5), nn.Linear(512, classes)).to(DEV)
+    ours = nn.Sequential(nn.Linear(width, 512), nn.GELU(), nn.Dropout(0.5), nn.Linear(512, classes)).to(DEV)
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(batch, width, device=DEV)
+    xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    dl = torch.randn(batch, classes, device=DEV)
+    ref.eval()  # dropout off on the comparator; ours gets training=False for the same effect
+    ref(xr).backward(dl)
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16, enabled=lp):
+        out = classifier_head(xo, ours, training=False)
+    out.backward(dl)
+    tol = 2e-2 if lp else 1e-4
+    assert rel_err(out, ref(x)) < tol
+    assert rel_err(xo.grad, xr.grad) < tol
+    for po, pr in zip(ours.parameters(), ref.parameters()):
+        assert rel_err(po.grad, pr.grad) < tol
+    # training mode: inverted dropout on the hidden layer — finite, and E[out] unchanged in scale
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16, enabled=lp):
+        out_t = classifier_head(x.clone().requires_grad_(True), ours, training=True)
+    out_t.sum().backward()
+    assert torch.isfinite(out_t).all() and all(torch.isfinite(p.grad).all() for p in ours.parameters())
