@@ -95,3 +95,38 @@ def client_sizes(config: dict) -> List[int]:
             raise ValueError("federated.samples_per_client list must have num_clients entries")
         return [int(s) for s in spc]
     return [int(spc)] * k
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # reference data.py:33-34
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+class DeviceBatchAssembler:
+    """Batch assembly on the GPU (scope row f3): a loader that yields raw ``uint8`` pixels
+    (``image_u8`` [B,3,H,W] or [B,H,W,3], optional ``mask_u8`` [B,H,W]) instead of normalised fp32
+    tensors ships a quarter of the bytes over PCIe; ``fv_assemble_batch`` then does what the
+    reference Dataset does per sample on the host — ``TF.to_tensor`` + ``TF.normalize`` + mask to
+    +-1 + 4-channel concat (reference data.py:148-155, 222-224) — in one pass, writing the NCHW fp32
+    batch the patch-embedding TMA map reads. Batches that already carry ``image`` pass through.
+
+        for batch in loader:                       # host dicts, uint8
+            batch = assembler(batch)               # device dict with "image" fp32 [B,C,H,W]
+    """
+
+    def __init__(self, device: torch.device, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> None:
+        self.device = torch.device(device)
+        self.mean = [float(v) for v in mean]
+        self.std = [float(v) for v in std]
+
+    def __call__(self, batch: Dict) -> Dict:
+        from . import ops
+
+        if "image_u8" not in batch:
+            return batch
+        out = {k: v for k, v in batch.items() if k not in ("image_u8", "mask_u8")}
+        img = batch["image_u8"].to(self.device, non_blocking=True).contiguous()
+        mask = batch.get("mask_u8")
+        if mask is not None:
+            mask = mask.to(self.device, non_blocking=True).contiguous()
+        out["image"] = ops.assemble_batch(img, mask, self.mean, self.std, None, 1.0, ops.MIX_NONE, [0, 0, 0, 0])
+        return out

@@ -464,3 +464,84 @@ def fedavg_accum(acc: Tensor, w: Tensor, weight: float, init: bool) -> None:
 def cast_bf16(src: Tensor, dst: Tensor) -> None:
     _need_cuda(src, dst)
     LIB.call("fv_cast_f32_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream(src))
+
+
+# ------------------------------------------------------------------------------------------------
+# device-side batch assembly (scope row f3)
+# ------------------------------------------------------------------------------------------------
+MIX_NONE, MIX_MIXUP, MIX_CUTMIX = 0, 1, 2
+
+
+def _mix_args(perm: Optional[Tensor], lam: float, mode: int, box, batch: int):
+    if mode not in (MIX_NONE, MIX_MIXUP, MIX_CUTMIX):
+        raise FedVitError("mix: mode must be 0 (none), 1 (mixup) or 2 (cutmix)")
+    if mode != MIX_NONE:
+        if perm is None or perm.dtype != torch.int64 or perm.numel() != batch or not perm.is_cuda:
+            raise FedVitError("mix: perm must be a CUDA int64 tensor with one partner index per sample")
+        perm = perm.contiguous()
+    x1, y1, x2, y2 = (int(v) for v in box)
+    # the two mixing weights exactly as torch forms them: the python scalars lam and (1 - lam), each
+    # rounded to fp32 when it meets the fp32 tensor
+    return perm, float(lam), float(1.0 - lam), x1, y1, x2, y2
+
+
+@torch.library.custom_op("fedvit::mix_batch", mutates_args=())
+def mix_batch(x: Tensor, perm: Optional[Tensor], lam: float, mode: int, box: List[int]) -> Tensor:
+    """MixUp (mode 1: ``lam*x + (1-lam)*x[perm]``) or CutMix (mode 2: rows box[0]:box[2] x columns
+    box[1]:box[3] taken from ``x[perm]``) of an fp32 NCHW batch in one pass — reference
+    utils.py:112-150. Bit-identical to the reference's ATen expression."""
+    _need_cuda(x, perm)
+    if x.dim() != 4 or x.dtype != torch.float32 or not x.is_contiguous() or x.shape[3] % 4:
+        raise FedVitError("mix_batch: x must be contiguous fp32 [B,C,H,W] with W % 4 == 0")
+    b, c, h, w = x.shape
+    perm, lam_, oml, x1, y1, x2, y2 = _mix_args(perm, lam, mode, box, b)
+    out = torch.empty_like(x)
+    LIB.call("fv_mix_batch", x.data_ptr(), _ptr(perm), lam_, oml, mode, x1, y1, x2, y2, out.data_ptr(), b, c, h, w,
+             _stream(x))
+    return out
+
+
+@mix_batch.register_fake
+def _(x, perm, lam, mode, box):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("fedvit::assemble_batch", mutates_args=())
+def assemble_batch(img_u8: Tensor, mask_u8: Optional[Tensor], mean: List[float], std: List[float],
+                   perm: Optional[Tensor], lam: float, mode: int, box: List[int]) -> Tensor:
+    """uint8 images ([B,3,H,W] or [B,H,W,3]) + optional uint8 masks [B,H,W] -> normalised fp32 NCHW
+    with 3 or 4 channels (reference data.py:148-155, 222-224), optionally MixUp / CutMix-ed in the
+    same pass."""
+    _need_cuda(img_u8, mask_u8, perm)
+    if img_u8.dim() != 4 or img_u8.dtype != torch.uint8 or not img_u8.is_contiguous():
+        raise FedVitError("assemble_batch: images must be a contiguous uint8 4-D tensor")
+    nhwc = img_u8.shape[3] == 3 and img_u8.shape[1] != 3
+    if not nhwc and img_u8.shape[1] != 3:
+        raise FedVitError("assemble_batch: images must be [B,3,H,W] or [B,H,W,3]")
+    b = img_u8.shape[0]
+    h, w = (img_u8.shape[1], img_u8.shape[2]) if nhwc else (img_u8.shape[2], img_u8.shape[3])
+    if w % 4:
+        raise FedVitError("assemble_batch: width must be a multiple of 4")
+    if mask_u8 is not None and (mask_u8.dtype != torch.uint8 or tuple(mask_u8.shape) != (b, h, w)
+                                or not mask_u8.is_contiguous()):
+        raise FedVitError("assemble_batch: masks must be contiguous uint8 [B,H,W]")
+    if len(mean) != 3 or len(std) != 3:
+        raise FedVitError("assemble_batch: mean / std need three values")
+    perm, lam_, oml, x1, y1, x2, y2 = _mix_args(perm, lam, mode, box, b)
+    import ctypes
+
+    mean_c = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    std_c = (ctypes.c_float * 3)(*[float(v) for v in std])
+    out = torch.empty((b, 4 if mask_u8 is not None else 3, h, w), device=img_u8.device, dtype=torch.float32)
+    LIB.call("fv_assemble_batch", img_u8.data_ptr(), int(nhwc), _ptr(mask_u8), ctypes.addressof(mean_c),
+             ctypes.addressof(std_c), _ptr(perm), lam_, oml, mode, x1, y1, x2, y2, out.data_ptr(), b, h, w,
+             _stream(img_u8))
+    return out
+
+
+@assemble_batch.register_fake
+def _(img_u8, mask_u8, mean, std, perm, lam, mode, box):
+    nhwc = img_u8.shape[3] == 3 and img_u8.shape[1] != 3
+    b = img_u8.shape[0]
+    h, w = (img_u8.shape[1], img_u8.shape[2]) if nhwc else (img_u8.shape[2], img_u8.shape[3])
+    return img_u8.new_empty((b, 4 if mask_u8 is not None else 3, h, w), dtype=torch.float32)

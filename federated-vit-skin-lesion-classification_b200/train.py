@@ -42,7 +42,8 @@ from .fedavg import FedAvgAggregator, broadcast_initial, clients_of_rank, dist_i
 from .losses import build_loss
 from .model import build_model, count_parameters, get_layerwise_lr_groups
 from .optim import FusedAdamW
-from .utils import EMA, WarmupCosineScheduler, clip_grad_norm, get_device, load_config, seed_everything
+from .utils import (EMA, MixupCutmix, WarmupCosineScheduler, clip_grad_norm, get_device, load_config,
+                    mixup_criterion, seed_everything)
 
 
 def setup_logging(log_dir: Optional[str] = None, tag: str = "fed") -> logging.Logger:
@@ -136,9 +137,12 @@ def train_one_epoch(model: nn.Module, loader, criterion, optimizer, scheduler, s
     accum = max(1, int(t.get("gradient_accumulation_steps", 1)))
     use_meta = config.get("model", {}).get("metadata", {}).get("enabled", True)
     aug = config.get("augmentation", {})
-    if aug.get("mixup", {}).get("alpha", 0.0) > 0 or aug.get("cutmix", {}).get("prob", 0.0) > 0:
-        raise NotImplementedError("MixUp/CutMix are host-side augmentation outside this path "
-                                  "(SURVEY.md §2); set augmentation.mixup.alpha: 0 and cutmix.prob: 0")
+    mixer = None  # MixUp / CutMix exactly as the reference wires them (train.py:115-124,139-150)
+    mixup_a = aug.get("mixup", {}).get("alpha", 0.0)
+    cutmix_p = aug.get("cutmix", {}).get("prob", 0.0)
+    if mixup_a > 0 or cutmix_p > 0:
+        mixer = MixupCutmix(mixup_alpha=mixup_a, cutmix_alpha=aug.get("cutmix", {}).get("alpha", 1.0),
+                            cutmix_prob=cutmix_p)
 
     loss_sum = torch.zeros((), device=device, dtype=torch.float32)
     seen = 0
@@ -155,9 +159,14 @@ def train_one_epoch(model: nn.Module, loader, criterion, optimizer, scheduler, s
         images, labels, meta = batch["image"], batch["label"], batch.get("metadata")
         bs = images.size(0)
 
+        if mixer is not None:
+            images, labels_a, labels_b, lam = mixer(images, labels)
         with torch.amp.autocast(device_type=device.type, enabled=use_amp, dtype=amp_dtype):
             logits = model(images, metadata=meta if use_meta else None)["logits"]
-            loss = criterion(logits, labels) / accum
+            if mixer is not None:
+                loss = mixup_criterion(criterion, logits, labels_a, labels_b, lam) / accum
+            else:
+                loss = criterion(logits, labels) / accum
 
         if scaler is not None:
             scaler.scale(loss).backward()

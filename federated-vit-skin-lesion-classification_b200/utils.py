@@ -2,7 +2,7 @@
 for it (EMA, clip_grad_norm, WarmupCosineScheduler, seed_everything, get_device, load_config,
 checkpoint save/load), re-implemented over the flat arena.
 
-Out of scope here: MixUp/CutMix, TTA evaluation, auto batch-size probing, the
+Out of scope here: TTA evaluation, auto batch-size probing, the
 sklearn metric tables — they are host-side data/driver code, not the hot path.
 """
 from __future__ import annotations
@@ -205,3 +205,69 @@ def load_checkpoint(path, model, optimizer=None, scheduler=None, ema=None, devic
     if ema and ckpt.get("ema_state_dict"):
         ema.load_state_dict(ckpt["ema_state_dict"])
     return ckpt
+
+
+# ================================================================================================
+# MixUp / CutMix on the device (scope row f3) — reference utils.py:112-170, same names
+# ================================================================================================
+class MixUp:
+    """``mixed = lam * images + (1 - lam) * images[idx]`` (reference utils.py:112-121) as ONE pass
+    of ``fv_mix_batch`` instead of three ATen kernels + a gather; same random draws in the same
+    order (np.random.beta, torch.randperm on the images' device), bit-identical output."""
+
+    def __init__(self, alpha: float = 0.4):
+        self.alpha = alpha
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor):
+        lam = np.random.beta(self.alpha, self.alpha) if self.alpha > 0 else 1.0
+        idx = torch.randperm(images.size(0), device=images.device)
+        mixed = ops.mix_batch(images.float().contiguous(), idx, float(lam), ops.MIX_MIXUP, [0, 0, 0, 0])
+        return mixed, labels, labels[idx], lam
+
+
+class CutMix:
+    """Reference utils.py:124-150: a random box (rows x1:x2 of dim 2, columns y1:y2 of dim 3 — the
+    reference's naming) is pasted from the permuted batch; lam is recomputed from the box area."""
+
+    def __init__(self, alpha: float = 1.0, prob: float = 0.7):
+        self.alpha = alpha
+        self.prob = prob
+
+    @staticmethod
+    def _rand_bbox(size, lam):
+        W, H = size[2], size[3]
+        cut = np.sqrt(1. - lam)
+        cw, ch = int(W * cut), int(H * cut)
+        cx, cy = np.random.randint(W), np.random.randint(H)
+        x1, y1 = np.clip(cx - cw // 2, 0, W), np.clip(cy - ch // 2, 0, H)
+        x2, y2 = np.clip(cx + cw // 2, 0, W), np.clip(cy + ch // 2, 0, H)
+        return int(x1), int(y1), int(x2), int(y2)
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor):
+        if np.random.rand() > self.prob:
+            return images, labels, labels, 1.0
+        lam = np.random.beta(self.alpha, self.alpha)
+        idx = torch.randperm(images.size(0), device=images.device)
+        x1, y1, x2, y2 = self._rand_bbox(images.size(), lam)
+        mixed = ops.mix_batch(images.float().contiguous(), idx, 1.0, ops.MIX_CUTMIX, [x1, y1, x2, y2])
+        lam = 1 - ((x2 - x1) * (y2 - y1) / (images.size(-1) * images.size(-2)))
+        return mixed, labels, labels[idx], lam
+
+
+class MixupCutmix:
+    """Randomly choose MixUp or CutMix each batch (reference utils.py:153-164)."""
+
+    def __init__(self, mixup_alpha=0.4, cutmix_alpha=1.0, cutmix_prob=0.7):
+        self.mixup = MixUp(alpha=mixup_alpha)
+        self.cutmix = CutMix(alpha=cutmix_alpha, prob=1.0)
+        self.cutmix_prob = cutmix_prob
+
+    def __call__(self, images, labels):
+        if np.random.rand() < self.cutmix_prob:
+            return self.cutmix(images, labels)
+        return self.mixup(images, labels)
+
+
+def mixup_criterion(criterion, logits, labels_a, labels_b, lam):
+    """Reference utils.py:167-168."""
+    return lam * criterion(logits, labels_a) + (1 - lam) * criterion(logits, labels_b)

@@ -169,6 +169,26 @@ int fv_colsum(const void* a, int a_dtype, int64_t lda, float* out, int accumulat
               int64_t rows, int64_t cols, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Device-side batch assembly (scope row f3).
+ * fv_assemble_batch replaces the per-sample tensor work of the reference Dataset
+ * (data.py:148-155 TF.to_tensor + TF.normalize + (mask-0.5)/0.5, data.py:222-224 torch.cat to 4
+ * channels) for a whole batch that crossed PCIe as bytes, optionally mixing in the same pass.
+ * fv_mix_batch replaces MixUp.__call__ / CutMix.__call__ (utils.py:112-150) on an fp32 batch.
+ *   img   uint8, nhwc ? [B,H,W,3] : [B,3,H,W];  mask uint8 [B,H,W] or NULL (-> 3 channels)
+ *   mean / stdv  HOST pointers to 3 floats (IMAGENET_MEAN / IMAGENET_STD in the reference)
+ *   perm  int64 [B] device: partner sample of each sample (torch.randperm), NULL when mode == 0
+ *   mode  0 none, 1 mixup: out = lam*x + one_minus_lam*x[perm] (two rounded products + rounded sum,
+ *         bit-identical to torch), 2 cutmix: rows [x1,x2) x columns [y1,y2) taken from x[perm]
+ *   out   fp32 [B, 3|4, H, W];  W % 4 == 0
+ * ---------------------------------------------------------------------------------------- */
+int fv_assemble_batch(const uint8_t* img, int nhwc, const uint8_t* mask, const float* mean, const float* stdv,
+                      const int64_t* perm, float lam, float one_minus_lam, int mode, int x1, int y1, int x2, int y2,
+                      float* out, int64_t batch, int64_t height, int64_t width, void* stream);
+int fv_mix_batch(const float* x, const int64_t* perm, float lam, float one_minus_lam, int mode, int x1, int y1,
+                 int x2, int y2, float* out, int64_t batch, int64_t chans, int64_t height, int64_t width,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Losses. fv_asl_loss replaces AsymmetricFocalLoss.forward (losses.py:41-67) AND its autograd
  * backward in one pass; fv_ce_loss replaces F.cross_entropy (utils.py:262).
  *   logits fp32 [B,C] (C <= 32), targets int64 [B]

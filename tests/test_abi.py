@@ -11,11 +11,12 @@ def test_header_parses_and_lists_the_path():
     protos = _lib.parse_header()
     for name in ["fv_gemm_bf16", "fv_gemm_f32", "fv_layernorm_fwd", "fv_layernorm_bwd", "fv_attention_fwd",
                  "fv_attention_bwd", "fv_asl_loss", "fv_ce_loss", "fv_adamw_flat", "fv_sumsq",
-                 "fv_fedavg_accum", "fv_patchify", "fv_colsum", "fv_last_error", "fv_launch_count"]:
+                 "fv_fedavg_accum", "fv_patchify", "fv_colsum", "fv_assemble_batch", "fv_mix_batch", "fv_last_error",
+                 "fv_launch_count"]:
         assert name in protos, name
     # plain C only: no C++ / torch types may appear in any signature
     allowed = {"int", "int64_t", "float", "size_t", "void*", "const void*", "float*", "const float*",
-               "const int64_t*", "int64_t*", "const char*"}
+               "const int64_t*", "int64_t*", "const char*", "const uint8_t*"}
     for name, (ret, args) in protos.items():
         assert ret in allowed, (name, ret)
         for t, _ in args:

@@ -337,3 +337,67 @@ def test_patch_embed_im2col_free(B, C, S, D):
     got = x.view(B, N, D)
     assert rel_err(got[:, 1:], ref) < 2e-3
     assert float((got[:, 0] - 7.0).abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# device-side batch assembly, MixUp / CutMix (scope row f3) — bit-exact against the reference fixture
+# ------------------------------------------------------------------------------------------------
+def test_mix_and_assemble_match_reference_fixture_bit_exactly():
+    import numpy as np
+    from conftest import GOLDEN
+    from oracle import mix
+
+    g = dict(np.load(GOLDEN / "mix.npz"))
+    x = torch.from_numpy(g["x"]).to(DEV)
+    idx = torch.from_numpy(g["mixup/idx"]).to(DEV)
+    out = ops.mix_batch(x, idx, float(g["mixup/lam"]), ops.MIX_MIXUP, [0, 0, 0, 0])
+    assert torch.equal(out.cpu(), torch.from_numpy(g["mixup/out"]))
+    box = mix.rand_bbox(x.shape, float(g["cutmix/lam0"]), int(g["cutmix/cx"]), int(g["cutmix/cy"]))
+    out = ops.mix_batch(x, torch.from_numpy(g["cutmix/idx"]).to(DEV), 1.0, ops.MIX_CUTMIX, list(box))
+    assert torch.equal(out.cpu(), torch.from_numpy(g["cutmix/out"]))
+    assert torch.equal(ops.mix_batch(x, None, 1.0, ops.MIX_NONE, [0, 0, 0, 0]), x)
+    # uint8 -> normalised fp32, NHWC (PIL order) and planar, with and without the mask plane
+    img = torch.from_numpy(g["asm/img_u8"]).to(DEV)
+    mask = torch.from_numpy(g["asm/mask_u8"]).to(DEV)
+    want = torch.from_numpy(g["asm/out"])
+    mean, std = list(mix.IMAGENET_MEAN), list(mix.IMAGENET_STD)
+    assert torch.equal(ops.assemble_batch(img, mask, mean, std, None, 1.0, 0, [0, 0, 0, 0]).cpu(), want)
+    planar = img.permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(ops.assemble_batch(planar, None, mean, std, None, 1.0, 0, [0, 0, 0, 0]).cpu(), want[:, :3])
+    # assembly + mixing in one pass == assembly, then the oracle's mixing
+    perm = torch.tensor([3, 0, 4, 1, 2], device=DEV)
+    fused = ops.assemble_batch(img, mask, mean, std, perm, 0.3, ops.MIX_MIXUP, [0, 0, 0, 0]).cpu().numpy()
+    assert np.array_equal(fused, mix.mixup(g["asm/out"], perm.cpu().numpy(), 0.3))
+    fused = ops.assemble_batch(planar, mask, mean, std, perm, 1.0, ops.MIX_CUTMIX, [5, 9, 20, 30]).cpu().numpy()
+    assert np.array_equal(fused, mix.cutmix(g["asm/out"], perm.cpu().numpy(), (5, 9, 20, 30))[0])
+
+
+def test_mixup_cutmix_classes_follow_reference_draw_order():
+    """fedvit_b200.utils.MixUp / CutMix / MixupCutmix make the reference's random draws in the
+    reference's order (utils.py:112-164), so a seeded run mixes the same pairs with the same lam."""
+    import numpy as np
+    from fedvit_b200 import utils
+    from oracle import mix
+
+    x = torch.randn(16, 3, 224, 224, device=DEV)
+    y = torch.arange(16, device=DEV) % 7
+    np.random.seed(3)
+    torch.manual_seed(3)
+    mixed, la, lb, lam = utils.MixUp(alpha=0.4)(x, y)
+    np.random.seed(3)
+    torch.manual_seed(3)
+    lam_ref = np.random.beta(0.4, 0.4)
+    idx = torch.randperm(16, device=DEV)
+    assert lam == lam_ref and torch.equal(lb, y[idx]) and torch.equal(la, y)
+    assert torch.equal(mixed, lam_ref * x + (1 - lam_ref) * x[idx])  # the reference's ATen expression
+    np.random.seed(4)
+    torch.manual_seed(4)
+    mixed, la, lb, lam = utils.CutMix(alpha=1.0, prob=1.0)(x, y)
+    np.random.seed(4)
+    torch.manual_seed(4)
+    np.random.rand()
+    lam0 = np.random.beta(1.0, 1.0)
+    idx = torch.randperm(16, device=DEV)
+    box = mix.rand_bbox(x.shape, lam0, np.random.randint(224), np.random.randint(224))
+    want, lam_want = mix.cutmix(x.cpu().numpy(), idx.cpu().numpy(), box)
+    assert lam == lam_want and np.array_equal(mixed.cpu().numpy(), want) and torch.equal(lb, y[idx])

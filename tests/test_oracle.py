@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import micro_config, rel_err, state_from_golden
+from conftest import GOLDEN, micro_config, rel_err, state_from_golden
 from oracle import asl, fedavg, isic, ref_bridge, step
 from oracle.timm.models.vision_transformer import create_model
 
@@ -151,3 +151,22 @@ def test_fedavg_oracle_order_and_properties():
     sd = [{"w": f, "steps": torch.tensor(i)} for i, f in enumerate(flats)]
     out = fedavg.fedavg_state_dicts(sd, n_k)
     assert torch.equal(out["w"], a) and int(out["steps"]) == 0  # integer buffers from client 0
+
+
+# ------------------------------------------------------------------------------------------------
+# batch assembly / MixUp / CutMix restatement (oracle/mix.py) against the reference's own classes
+# ------------------------------------------------------------------------------------------------
+def test_mix_oracle_reproduces_reference_fixture():
+    """tests/golden/mix.npz was written by the reference's utils.MixUp / utils.CutMix and the
+    torchvision calls of its Dataset (tests/golden/make_golden_mix.py); the numpy restatement has
+    to reproduce it bit for bit."""
+    from oracle import mix
+
+    g = dict(np.load(GOLDEN / "mix.npz"))
+    x = g["x"]
+    assert np.array_equal(mix.mixup(x, g["mixup/idx"], float(g["mixup/lam"])), g["mixup/out"])
+    box = mix.rand_bbox(x.shape, float(g["cutmix/lam0"]), int(g["cutmix/cx"]), int(g["cutmix/cy"]))
+    out, lam = mix.cutmix(x, g["cutmix/idx"], box)
+    assert np.array_equal(out, g["cutmix/out"]) and lam == float(g["cutmix/lam_out"])
+    assert np.array_equal(mix.assemble(g["asm/img_u8"], g["asm/mask_u8"], nhwc=True), g["asm/out"])
+    assert np.array_equal(mix.assemble(g["asm/img_u8"].transpose(0, 3, 1, 2).copy(), None)[:, :3], g["asm/out"][:, :3])
