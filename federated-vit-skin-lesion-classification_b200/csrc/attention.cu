@@ -486,6 +486,19 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
 int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                      int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
 
+int attention_tc_fwd_long(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
+                          float scale, cudaStream_t stream);
+
+static bool attention_forced_legacy() {
+  static int forced = -1;  // FEDVIT_ATTN=legacy keeps every length on the mma.sync kernels (A/B checks)
+  if (forced < 0) {
+    const char* e = getenv("FEDVIT_ATTN");
+    forced = (e != nullptr && e[0] == 'l') ? 1 : 0;
+  }
+  return forced == 1;
+}
+static bool use_tc_attention_long(int64_t tokens) { return !attention_forced_legacy() && tokens > 256 && tokens <= 768; }
+
 static bool use_tc_attention(int64_t tokens) {
   static int forced = -1;  // FEDVIT_ATTN=legacy keeps every length on the mma.sync kernels (A/B checks)
   if (forced < 0) {
@@ -510,6 +523,8 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
                "fv_attention_fwd: pointers must be 16-byte aligned");
   if (use_tc_attention(tokens))
     return attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
+  if (use_tc_attention_long(tokens))
+    return attention_tc_fwd_long(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
   dim3 grid(static_cast<unsigned>(ceil_div(tokens, AT_T)), static_cast<unsigned>(batch * heads));
   FV_CHECK_CUDA(fv::launch_pdl(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse,

@@ -757,4 +757,300 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
   return FV_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// long sequences (256 < N <= 768: ViT-L/16 @ 384 has 577 tokens): forward
+// ---------------------------------------------------------------------------------------------
+// One persistent CTA per SM walks (batch, head) items. K and V of the item stay resident in shared
+// memory as 128-key tiles; the 128-query tiles stream through a two-slot ring. Exact two-pass
+// softmax per query tile, no online rescaling:
+//   pass A  S_j = Q K_j^T for every key block j  -> row maxima
+//   pass B  S_j again -> P_j = exp2(scale*log2e*(S_j - max)) written back into TMEM as packed bf16
+//           -> O += P_j V_j  (A operand from TMEM, accumulated in TMEM across the key blocks)
+// The score MMA is the cheap part (the softmax's MUFU work sets the pace), so recomputing it costs
+// less than the rescale traffic of the online form. S is double-buffered (2 x 128 TMEM columns):
+// the MMA of block j+1 runs while the softmax warps work on block j.
+constexpr int ATL_THREADS = 192;  // warps 0-3 softmax / epilogue, warp 4 MMA issue, warp 5 TMEM alloc + TMA producer
+constexpr int ATL_MAX_KB = 6;     // 768 keys
+constexpr int ATL_TILE = 128 * 128;  // one [128 x 64] bf16 tile
+
+struct AttnLongParams {
+  int N, H, kw, nkb, nqt, items;
+  float scale;
+  __nv_bfloat16* out;
+  float* lse;
+};
+
+__global__ void __launch_bounds__(ATL_THREADS, 1)
+attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tmap, const AttnLongParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                        // 2 slots
+  uint8_t* sK = sQ + 2 * ATL_TILE;           // nkb tiles
+  uint8_t* sV = sK + p.nkb * ATL_TILE;       // nkb tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.nkb * ATL_TILE);
+  uint64_t* bar_k = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_kfree = bars + 2;
+  uint64_t* bar_vfree = bars + 3;
+  uint64_t* bar_q = bars + 4;       // [2]
+  uint64_t* bar_qfree = bars + 6;   // [2]
+  uint64_t* bar_s = bars + 8;       // [2] score buffer full
+  uint64_t* bar_free = bars + 10;   // [2] score buffer consumed by the softmax warps
+  uint64_t* bar_p = bars + 12;      // [2] P of a pass-B block written; ping-pong: a warp without live rows
+                                    // runs one block ahead, its early arrival must not count for this block
+  uint64_t* bar_o = bars + 14;
+  uint64_t* bar_odone = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hd = p.H * 64;
+  const int nkb = p.nkb, nqt = p.nqt;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_kfree, 1);
+    mbar_init(bar_vfree, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_q[i], 1);
+      mbar_init(&bar_qfree[i], 1);
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_free[i], 128);
+    }
+    mbar_init(&bar_p[0], 128);
+    mbar_init(&bar_p[1], 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_odone, 128);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  constexpr uint32_t T_O = 256;
+
+  if (warp == 5) {
+    // ------------------------------ TMA producer ------------------------------------------------
+    int n = 0, gt = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      const int b = item / p.H, h = item % p.H;
+      if (n > 0) mbar_wait(bar_kfree, (n - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_k, nkb * ATL_TILE);
+        for (int j = 0; j < nkb; ++j) tma_load_3d(sK + j * ATL_TILE, &tmap, bar_k, hd + h * 64, j * 128, b);
+      }
+      __syncwarp();
+      if (n > 0) mbar_wait(bar_vfree, (n - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_v, nkb * ATL_TILE);
+        for (int j = 0; j < nkb; ++j) tma_load_3d(sV + j * ATL_TILE, &tmap, bar_v, 2 * hd + h * 64, j * 128, b);
+      }
+      __syncwarp();
+      for (int t = 0; t < nqt; ++t, ++gt) {
+        const int slot = gt & 1;
+        if (gt >= 2) mbar_wait(&bar_qfree[slot], ((gt >> 1) - 1) & 1);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_q[slot], ATL_TILE);
+          tma_load_3d(sQ + slot * ATL_TILE, &tmap, &bar_q[slot], h * 64, t * 128, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------ MMA issue (whole warp, elected lane issues) -----------------
+    const uint32_t idesc_o = make_idesc(kFmtBF16, 0, 1, 128, 64);
+    int n = 0, gt = 0, u = 0, pb = 0;  // items, query tiles, score-buffer uses, pass-B blocks so far
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      mbar_wait(bar_k, n & 1);
+      for (int t = 0; t < nqt; ++t, ++gt) {
+        const int slot = gt & 1;
+        mbar_wait(&bar_q[slot], (gt >> 1) & 1);
+        const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + slot * ATL_TILE), 16, 1024);
+        auto issue_s = [&](int j) {
+          const int buf = u & 1;
+          mbar_wait(&bar_free[buf], ((u >> 1) & 1) ^ 1);  // the buffer's previous tenant has been read
+          tc_fence_after();
+          int kwb = p.kw - j * 128;
+          if (kwb > 128) kwb = 128;
+          const uint32_t idesc_s = make_idesc(kFmtBF16, 0, 0, 128, kwb);
+          const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + j * ATL_TILE), 16, 1024);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem + buf * 128, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&bar_s[buf]);
+          }
+          __syncwarp();
+          ++u;
+        };
+        auto issue_pv = [&](int j, int buf, bool last) {
+          mbar_wait(&bar_p[pb & 1], (pb >> 1) & 1);
+          ++pb;
+          tc_fence_after();
+          int kwb = p.kw - j * 128;
+          if (kwb > 128) kwb = 128;
+          const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + j * ATL_TILE), 64 * 128, 1024);
+          const int ksteps = kwb >> 4;
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_ts(tmem + T_O, tmem + buf * 128 + k * 8, dv + k * (2048 >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            if (last) {
+              umma_commit(bar_o);
+              if (t == nqt - 1) umma_commit(bar_vfree);
+            }
+          }
+          __syncwarp();
+        };
+        for (int j = 0; j < nkb; ++j) issue_s(j);  // pass A: scores for the row maxima
+        const int u0 = u;
+        for (int j = 0; j < nkb; ++j) {            // pass B: scores again, PV one block behind
+          issue_s(j);
+          if (j == nkb - 1 && elect_one()) {
+            umma_commit(&bar_qfree[slot]);            // this query tile's last reader
+            if (t == nqt - 1) umma_commit(bar_kfree);
+          }
+          __syncwarp();
+          if (j == 0) {
+            if (t == 0) mbar_wait(bar_v, n & 1);
+            if (gt > 0) mbar_wait(bar_odone, (gt - 1) & 1);  // previous tile's O has left TMEM
+          } else {
+            issue_pv(j - 1, (u0 + j - 1) & 1, false);
+          }
+        }
+        issue_pv(nkb - 1, (u0 + nkb - 1) & 1, true);
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------ softmax + epilogue -------------------------------------------
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const float sl2 = p.scale * ATC_LOG2E;
+    int gt = 0, u = 0, pb = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int b = item / p.H, h = item % p.H;
+      for (int t = 0; t < nqt; ++t, ++gt) {
+        const int q = t * 128 + warp * 32 + lane;
+        const bool warp_live = t * 128 + warp * 32 < p.N;  // warp-uniform
+        float mx = -INFINITY, sum = 0.f;
+        for (int pass = 0; pass < 2; ++pass) {
+          const float mxs = mx * sl2;
+          for (int j = 0; j < nkb; ++j, ++u) {
+            const int buf = u & 1;
+            mbar_wait(&bar_s[buf], (u >> 1) & 1);
+            tc_fence_after();
+            if (warp_live) {
+              int kwb = p.kw - j * 128;
+              if (kwb > 128) kwb = 128;
+              const int nch = (kwb + 31) >> 5;
+              for (int c = 0; c < nch; ++c) {
+                const int key0 = j * 128 + c * 32;
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + buf * 128 + c * 32, r);
+                tmem_ld_wait();
+                if (pass == 0) {
+                  if (key0 + 32 <= p.N) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                      if (key0 + i < p.N) mx = fmaxf(mx, __uint_as_float(r[i]));
+                  }
+                } else {
+                  uint32_t pk[16];
+                  if (key0 + 32 <= p.N) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                      const float p0 = atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs));
+                      const float p1 = atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs));
+                      sum += p0 + p1;
+                      pk[i >> 1] = pack_bf16(p0, p1);
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                      const float p0 = (key0 + i < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i]), sl2, -mxs)) : 0.f;
+                      const float p1 = (key0 + i + 1 < p.N) ? atc_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs)) : 0.f;
+                      sum += p0 + p1;
+                      pk[i >> 1] = pack_bf16(p0, p1);
+                    }
+                  }
+                  tmem_st_32x16(taddr + buf * 128 + c * 16, pk);  // over columns this thread has consumed
+                }
+              }
+              if (pass == 1) tmem_st_wait();
+            }
+            tc_fence_before();
+            if (pass == 1) {
+              mbar_arrive(&bar_p[pb & 1]);
+              ++pb;
+            }
+            mbar_arrive(&bar_free[buf]);
+          }
+        }
+        mbar_wait(bar_o, gt & 1);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        if (warp_live) {
+          tmem_ld_32x32(taddr + T_O, o0);
+          tmem_ld_32x32(taddr + T_O + 32, o1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(bar_odone);
+        if (warp_live && q < p.N) {
+          const float inv = 1.0f / sum;
+          uint32_t w[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            w[i] = pack_bf16(__uint_as_float(o0[2 * i]) * inv, __uint_as_float(o0[2 * i + 1]) * inv);
+            w[16 + i] = pack_bf16(__uint_as_float(o1[2 * i]) * inv, __uint_as_float(o1[2 * i + 1]) * inv);
+          }
+          __nv_bfloat16* dst = p.out + ((static_cast<long long>(b) * p.N + q) * p.H + h) * 64;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) st_v8(dst + jj * 16, w + jj * 8);
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = mx * p.scale + logf(sum);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int attention_tc_fwd_long(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
+                          float scale, cudaStream_t stream) {
+  AttnLongParams p;
+  p.N = static_cast<int>(tokens);
+  p.H = static_cast<int>(heads);
+  p.kw = static_cast<int>((tokens + 15) / 16 * 16);
+  p.nkb = (p.kw + 127) / 128;
+  p.nqt = (p.N + 127) / 128;
+  p.items = static_cast<int>(batch * heads);
+  p.scale = scale;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  FV_CHECK_ARG(p.nkb <= ATL_MAX_KB, "attention_tc_fwd_long: at most %d tokens", ATL_MAX_KB * 128);
+  CUtensorMap map;
+  int rc = make_qkv_map(&map, qkv, batch, tokens, 3 * heads * 64, 128);
+  if (rc != FV_OK) return rc;
+  const int smem = (2 + 2 * p.nkb) * ATL_TILE + 1024 + 256;
+  static int configured = 0;
+  if (configured < smem) {
+    FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  FV_CHECK_CUDA(fv::launch_pdl(attn_tc_fwd_long_kernel, dim3(static_cast<unsigned>(grid)), dim3(ATL_THREADS), smem, stream,
+                               map, p));
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
 }  // namespace fv

@@ -257,7 +257,7 @@ def attention():
     from fedvit_b200 import ops
 
     res = {}
-    for (B, N, H) in [(2, 197, 3), (1, 577, 2), (3, 64, 1), (2, 65, 2)]:
+    for (B, N, H) in [(2, 197, 3), (1, 577, 2), (3, 64, 1), (2, 65, 2), (3, 257, 2), (2, 768, 1), (5, 400, 3)]:
         g = torch.Generator(device="cuda").manual_seed(N)
         qkv = (torch.randn(B * N, 3 * H * 64, device="cuda", generator=g)).bfloat16()
         dout = torch.randn(B * N, H * 64, device="cuda", generator=g).bfloat16()
@@ -289,6 +289,12 @@ def attention():
     ms = _time(lambda: ops.attention_bwd(qkv, out, dout, lse, B, N, H, 0.125))
     res["bwd_ms_vitb"] = ms
     res["bwd_tflops_alg"] = 10.0 * B * H * N * N * 64 / ms / 1e9
+    B, N, H = 64, 577, 16  # ViT-L/16 @ 384
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda").bfloat16()
+    dout = torch.randn(B * N, H * 64, device="cuda").bfloat16()
+    out, lse = ops.attention_fwd(qkv, B, N, H, 0.125)
+    res["fwd_ms_vitl384"] = _time(lambda: ops.attention_fwd(qkv, B, N, H, 0.125))
+    res["bwd_ms_vitl384"] = _time(lambda: ops.attention_bwd(qkv, out, dout, lse, B, N, H, 0.125))
     return res
 
 

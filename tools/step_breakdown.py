@@ -36,6 +36,7 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--backbone", type=str, default="vit_base_patch16_224")
     args = ap.parse_args()
     import torch
 
@@ -46,6 +47,9 @@ def main() -> None:
 
     dev = torch.device("cuda", 0)
     cfg = bench.model_config()
+    cfg["model"]["backbone"] = args.backbone
+    img = int(args.backbone.split("_")[-1])
+    cfg["model"]["image_size"] = img
     utils.seed_everything(42)
     net = model.build_model(cfg).to(dev).train()
     arena = FlatArena(net)
@@ -53,7 +57,7 @@ def main() -> None:
     opt = optim.FusedAdamW(model.get_layerwise_lr_groups(net, 1e-4, 0.75, 1e-5), weight_decay=1e-5, arena=arena)
     crit = losses.build_loss(cfg)
     B = args.batch
-    x = torch.randn(2 * B, 3, bench.IMG, bench.IMG, device=dev)
+    x = torch.randn(2 * B, 3, img, img, device=dev)
     y = torch.randint(0, bench.CLASSES, (2 * B,), device=dev)
 
     def step(i):
@@ -84,7 +88,7 @@ def main() -> None:
         d[0] += s.elapsed_time(e)
         d[1] += 1
         d[2] += fl
-    print(f"step {total:.3f} ms (with per-launch events), batch {B}; per step:")
+    print(f"{args.backbone}: step {total:.3f} ms (with per-launch events), batch {B}; per step:")
     print(f"{'ms/step':>9} {'share':>6} {'n':>4} {'us/launch':>10} {'TF/s':>7}  kernel")
     acc = 0.0
     for t, (ms, n, fl) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
