@@ -489,6 +489,11 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
 int attention_tc_fwd_long(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
                           float scale, cudaStream_t stream);
 
+int64_t attention_tc_bwd_long_workspace(int64_t batch, int64_t tokens, int64_t heads);
+int attention_tc_bwd_long(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                          void* workspace, int64_t batch, int64_t tokens, int64_t heads, float scale,
+                          cudaStream_t stream);
+
 static bool attention_forced_legacy() {
   static int forced = -1;  // FEDVIT_ATTN=legacy keeps every length on the mma.sync kernels (A/B checks)
   if (forced < 0) {
@@ -533,9 +538,15 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
   return FV_OK;
 }
 
+extern "C" int64_t fv_attention_bwd_workspace(int64_t batch, int64_t tokens, int64_t heads) {
+  using namespace fv;
+  return use_tc_attention_long(tokens) ? attention_tc_bwd_long_workspace(batch, tokens, heads) : 0;
+}
+
 extern "C" int fv_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                                 float* delta, void* dqkv, int dtype, int64_t batch, int64_t tokens,
-                                int64_t heads, float scale, void* stream) {
+                                int64_t heads, float scale, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
   using namespace fv;
   FV_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "fv_attention_bwd: null pointer");
   FV_CHECK_ARG(dtype == FV_BF16, "fv_attention_bwd: only FV_BF16 (fp32 is composed from fv_gemm_f32)");
@@ -549,6 +560,12 @@ extern "C" int fv_attention_bwd(const void* qkv, const void* out, const void* do
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta,
       rows, (int)tokens, (int)heads));
   FV_LAUNCH_CHECK();
+  if (use_tc_attention_long(tokens)) {
+    FV_CHECK_ARG(workspace != nullptr && workspace_bytes >= attention_tc_bwd_long_workspace(batch, tokens, heads) &&
+                     (reinterpret_cast<uintptr_t>(workspace) & 127) == 0,
+                 "fv_attention_bwd: needs a 128-byte aligned workspace of fv_attention_bwd_workspace() bytes");
+    return attention_tc_bwd_long(qkv, dout, lse, delta, dqkv, workspace, batch, tokens, heads, scale, st);
+  }
   dim3 grid(static_cast<unsigned>(ceil_div(tokens, AT_T)), static_cast<unsigned>(batch * heads));
   FV_CHECK_CUDA(fv::launch_pdl(attn_bwd_dq_kernel, dim3(grid), dim3(AT_THREADS), 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout), lse,

@@ -1053,4 +1053,450 @@ int attention_tc_fwd_long(const void* qkv, void* out, float* lse, int64_t batch,
   return FV_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// long sequences (256 < N <= 768): backward
+// ---------------------------------------------------------------------------------------------
+// Work item = (batch, head, 128-key block). K / V of the block stay resident (double-buffered across
+// items), the 128-query tiles with their dO stream through a two-slot ring. Per query tile, exactly
+// the iteration of the short kernel: S = Q K^T and dP = dO V^T into TMEM, P / dS through swizzled
+// smem tiles, then dV += P^T dO and dK += dS^T Q (accumulated in TMEM over the query tiles, stored
+// once per item as bf16) and the block's dQ contribution dS K into one of two TMEM buffers. That
+// contribution is a partial sum over key blocks: it leaves as fp32 through a per-warp staging tile
+// and a TMA reduce-add (cp.reduce.async.bulk.tensor .add) into an fp32 scratch [B, N, H*64], which
+// a small pass converts to bf16 into dqkv afterwards. delta = rowsum(dO * O) comes from the
+// attn_delta pre-pass. No recomputation of the probabilities (the two-sweep mma.sync path computes
+// them twice), no software atomics.
+constexpr int ATLB_THREADS = 320;  // warps 0-7 math, warp 8 MMA issue, warp 9 TMEM alloc + TMA producer
+
+struct AttnLongBwdParams {
+  int N, H, kw, nkb, nqt, items;
+  float scale;
+  const float* lse;
+  const float* delta;
+  __nv_bfloat16* dqkv;
+};
+
+__global__ void __launch_bounds__(ATLB_THREADS, 1)
+attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                        const __grid_constant__ CUtensorMap tmap_dq, const AttnLongBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sKV = smem;                       // 2 slots x {K, V}
+  uint8_t* sQD = sKV + 4 * ATB_TILE;         // 2 slots x {Q, dO}
+  uint8_t* sP = sQD + 4 * ATB_TILE;          // 2 column blocks of 64 keys
+  uint8_t* sdS = sP + 2 * ATB_TILE;          // 2 column blocks
+  uint8_t* sStg = sdS + 2 * ATB_TILE;        // 8 warps x 4 KiB: fp32 dQ tiles on their way to the TMA reduce
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 8 * 4096);
+  uint64_t* bar_kv = bars + 0;       // [2]
+  uint64_t* bar_kvfree = bars + 2;   // [2]
+  uint64_t* bar_qd = bars + 4;       // [2]
+  uint64_t* bar_qdfree = bars + 6;   // [2]
+  uint64_t* bar_s = bars + 8;
+  uint64_t* bar_p = bars + 9;
+  uint64_t* bar_m2 = bars + 10;
+  uint64_t* bar_dqfree = bars + 11;  // [2] dQ TMEM buffer drained
+  uint64_t* bar_kvdone = bars + 13;  // dK / dV of the finished item drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hd = p.H * 64;
+  const int nqt = p.nqt, nkb = p.nkb;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_dq);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_kv[i], 1);
+      mbar_init(&bar_kvfree[i], 1);
+      mbar_init(&bar_qd[i], 1);
+      mbar_init(&bar_qdfree[i], 1);
+      mbar_init(&bar_dqfree[i], 256);
+    }
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 256);
+    mbar_init(bar_m2, 1);
+    mbar_init(bar_kvdone, 256);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  constexpr uint32_t T_S = 0, T_DP = 128, T_DK = 256, T_DV = 320, T_DQ = 384;  // T_DQ: two 64-column buffers
+
+  // item -> (batch, head, key block): key blocks of one (batch, head) are consecutive items, so its
+  // Q / dO tiles are re-read from L2
+  auto decode = [&](int item, int& b, int& h, int& kb) {
+    kb = item % nkb;
+    const int bh = item / nkb;
+    h = bh % p.H;
+    b = bh / p.H;
+  };
+
+  if (warp == 9) {
+    // ------------------------------ TMA producer ------------------------------------------------
+    auto load_kv = [&](int n, int item) {
+      int b, h, kb;
+      decode(item, b, h, kb);
+      const int ks = n & 1;
+      if (n >= 2) mbar_wait(&bar_kvfree[ks], ((n >> 1) - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(&bar_kv[ks], 2 * ATB_TILE);
+        tma_load_3d(sKV + ks * 2 * ATB_TILE, &tmap_qkv, &bar_kv[ks], hd + h * 64, kb * 128, b);
+        tma_load_3d(sKV + ks * 2 * ATB_TILE + ATB_TILE, &tmap_qkv, &bar_kv[ks], 2 * hd + h * 64, kb * 128, b);
+      }
+      __syncwarp();
+    };
+    int n = 0, it = 0;
+    if (static_cast<int>(blockIdx.x) < p.items) load_kv(0, blockIdx.x);
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      int b, h, kb;
+      decode(item, b, h, kb);
+      for (int qt = 0; qt < nqt; ++qt, ++it) {
+        const int slot = it & 1;
+        if (it >= 2) mbar_wait(&bar_qdfree[slot], ((it >> 1) - 1) & 1);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_qd[slot], 2 * ATB_TILE);
+          tma_load_3d(sQD + slot * 2 * ATB_TILE, &tmap_qkv, &bar_qd[slot], h * 64, qt * 128, b);
+          tma_load_3d(sQD + slot * 2 * ATB_TILE + ATB_TILE, &tmap_do, &bar_qd[slot], h * 64, qt * 128, b);
+        }
+        __syncwarp();
+        if (qt == 0 && item + static_cast<int>(gridDim.x) < p.items) load_kv(n + 1, item + gridDim.x);  // next item's K / V early
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------ MMA issue (whole warp, elected lane issues) -----------------
+    const uint32_t id_dvk = make_idesc(kFmtBF16, 1, 1, 128, 64);  // A MN-major (P^T / dS^T), B MN-major
+    const uint32_t id_dq = make_idesc(kFmtBF16, 0, 1, 128, 64);   // A K-major (dS), B MN-major (K)
+    auto kwb_of = [&](int kb) {
+      int w = p.kw - kb * 128;
+      return w > 128 ? 128 : w;
+    };
+    auto issue_mma1 = [&](int ks, int slot, int kwb) {
+      const uint32_t id_s = make_idesc(kFmtBF16, 0, 0, 128, kwb);
+      const uint64_t dK_k = make_smem_desc_sw128(smem_u32(sKV + ks * 2 * ATB_TILE), 16, 1024);
+      const uint64_t dV_k = make_smem_desc_sw128(smem_u32(sKV + ks * 2 * ATB_TILE + ATB_TILE), 16, 1024);
+      const uint64_t dQ_k = make_smem_desc_sw128(smem_u32(sQD + slot * 2 * ATB_TILE), 16, 1024);
+      const uint64_t dO_k = make_smem_desc_sw128(smem_u32(sQD + slot * 2 * ATB_TILE + ATB_TILE), 16, 1024);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_S, dQ_k + k * 2, dK_k + k * 2, id_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T_DP, dO_k + k * 2, dV_k + k * 2, id_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+    };
+    int n = 0, it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      int b, h, kb;
+      decode(item, b, h, kb);
+      const int ks = n & 1;
+      const int kwb = kwb_of(kb);
+      const bool has_next = item + static_cast<int>(gridDim.x) < p.items;
+      if (n == 0) {
+        mbar_wait(&bar_kv[0], 0);
+        mbar_wait(&bar_qd[0], 0);
+        tc_fence_after();
+        issue_mma1(0, 0, kwb);
+      }
+      const uint64_t dK_mn = make_smem_desc_sw128(smem_u32(sKV + ks * 2 * ATB_TILE), ATB_TILE, 1024);  // MN-major view
+      for (int qt = 0; qt < nqt; ++qt, ++it) {
+        const int slot = it & 1;
+        const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQD + slot * 2 * ATB_TILE), ATB_TILE, 1024);
+        const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sQD + slot * 2 * ATB_TILE + ATB_TILE), ATB_TILE, 1024);
+        mbar_wait(bar_p, it & 1);  // P / dS tiles written, S / dP consumed
+        tc_fence_after();
+        // the next iteration's scores go first so its softmax math overlaps this MMA 2
+        if (qt + 1 < nqt) {
+          mbar_wait(&bar_qd[(it + 1) & 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_mma1(ks, (it + 1) & 1, kwb);
+        } else if (has_next) {
+          int b2, h2, kb2;
+          decode(item + gridDim.x, b2, h2, kb2);
+          mbar_wait(&bar_kv[(n + 1) & 1], ((n + 1) >> 1) & 1);
+          mbar_wait(&bar_qd[(it + 1) & 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_mma1((n + 1) & 1, (it + 1) & 1, kwb_of(kb2));
+        }
+        if (qt == 0 && n > 0) mbar_wait(bar_kvdone, (n - 1) & 1);  // previous item's dK / dV have left TMEM
+        if (it >= 2) mbar_wait(&bar_dqfree[it & 1], ((it >> 1) - 1) & 1);  // dQ buffer of iteration it-2 drained
+        tc_fence_after();
+        const uint64_t dP_mn = make_smem_desc_sw128(smem_u32(sP), ATB_TILE, 1024);
+        const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), ATB_TILE, 1024);
+        const uint64_t dS_k0 = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
+        const int ks16 = kwb >> 4;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + T_DV, dP_mn + k * 128, dO_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + T_DK, dS_mn + k * 128, dQ_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k < ks16) {
+              const uint64_t dS_k = dS_k0 + (((k >> 2) * ATB_TILE + (k & 3) * 32) >> 4);
+              umma_bf16(tmem + T_DQ + (it & 1) * 64, dS_k, dK_mn + k * 128, id_dq, k > 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_m2);
+          umma_commit(&bar_qdfree[slot]);
+          if (qt == nqt - 1) umma_commit(&bar_kvfree[ks]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------ math + output warps ----------------------------------------
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int r = quarter * 32 + lane;  // row inside the 128-row tile (TMEM lane)
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float sl2 = p.scale * ATC_LOG2E;
+    const long long rs = 3LL * hd;
+    uint8_t* stg = sStg + warp * 4096;
+    bool stg_pending = false;
+
+    // dK (group 0) / dV (group 1): this thread's row of 64 bf16 straight from registers
+    auto store_kv_row = [&](int b, int h, int kb) {
+      uint32_t o0[32], o1[32];
+      const uint32_t col = hf == 0 ? T_DK : T_DV;
+      tmem_ld_32x32(lane_base + col, o0);
+      tmem_ld_32x32(lane_base + col + 32, o1);
+      tmem_ld_wait();
+      const int tok = kb * 128 + r;
+      if (tok < p.N) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          w[i] = pack_bf16(__uint_as_float(o0[2 * i]), __uint_as_float(o0[2 * i + 1]));
+          w[16 + i] = pack_bf16(__uint_as_float(o1[2 * i]), __uint_as_float(o1[2 * i + 1]));
+        }
+        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * p.N + tok) * rs + (hf == 0 ? 1 : 2) * hd + h * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_v8(dst + j * 16, w + j * 8);
+      }
+    };
+    // this warp's 32 rows x 32 fp32 columns of a dQ partial tile -> staging -> TMA reduce-add
+    auto reduce_dq = [&](int buf, int b, int h, int qt) {
+      uint32_t v[32];
+      tmem_ld_32x32(lane_base + T_DQ + buf * 64 + hf * 32, v);
+      tmem_ld_wait();
+      if (stg_pending) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) =
+            make_uint4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_3d(&tmap_dq, stg, h * 64 + hf * 32, qt * 128 + quarter * 32, b);
+        tma_store_commit();
+      }
+      stg_pending = true;
+    };
+
+    int it = 0, n = 0;
+    int pb = 0, ph = 0, pqt = 0;              // (batch, head, query tile) of the previous iteration
+    bool pend_kv = false;
+    int kv_b = 0, kv_h = 0, kv_kb = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+      int b, h, kb;
+      decode(item, b, h, kb);
+      const float* lse_bh = p.lse + (static_cast<long long>(b) * p.H + h) * p.N;
+      const float* del_bh = p.delta + (static_cast<long long>(b) * p.H + h) * p.N;
+      for (int qt = 0; qt < nqt; ++qt, ++it) {
+        const int q = qt * 128 + r;
+        const float l2 = q < p.N ? __ldg(lse_bh + q) * ATC_LOG2E : INFINITY;  // in flight during the wait below
+        const float dl = q < p.N ? __ldg(del_bh + q) : 0.f;
+        mbar_wait(bar_s, it & 1);
+        tc_fence_after();
+        uint32_t pk[2][16], dk[2][16];
+        const bool rows_live = qt * 128 + quarter * 32 < p.N;  // warp-uniform
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int ch = 2 * c + hf;  // 32-key chunks dealt alternately to the two groups
+          const int key0 = kb * 128 + ch * 32;
+          if (!rows_live || key0 >= p.N) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { pk[c][i] = 0u; dk[c][i] = 0u; }
+            continue;
+          }
+          uint32_t s[32], d[32];
+          tmem_ld_32x32(lane_base + T_S + ch * 32, s);
+          tmem_ld_32x32(lane_base + T_DP + ch * 32, d);
+          tmem_ld_wait();
+          if (key0 + 32 <= p.N) {
+            const float dls = dl * p.scale;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
+              const float p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
+              const float s0 = p0 * fmaf(__uint_as_float(d[i]), p.scale, -dls);
+              const float s1 = p1 * fmaf(__uint_as_float(d[i + 1]), p.scale, -dls);
+              pk[c][i >> 1] = pack_bf16(p0, p1);
+              dk[c][i >> 1] = pack_bf16(s0, s1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = 0.f, p1 = 0.f, s0 = 0.f, s1 = 0.f;
+              if (key0 + i < p.N) {
+                p0 = atc_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2));
+                s0 = p0 * (__uint_as_float(d[i]) - dl) * p.scale;
+              }
+              if (key0 + i + 1 < p.N) {
+                p1 = atc_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2));
+                s1 = p1 * (__uint_as_float(d[i + 1]) - dl) * p.scale;
+              }
+              pk[c][i >> 1] = pack_bf16(p0, p1);
+              dk[c][i >> 1] = pack_bf16(s0, s1);
+            }
+          }
+        }
+        if (it > 0) {
+          mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 retired: sP / sdS free, its dQ / dK / dV final
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint8_t* prow = sP + c * ATB_TILE + r * 128;
+          uint8_t* srow = sdS + c * ATB_TILE + r * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int unit = (hf * 4 + u) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + (unit << 4)) =
+                make_uint4(pk[c][u * 4], pk[c][u * 4 + 1], pk[c][u * 4 + 2], pk[c][u * 4 + 3]);
+            *reinterpret_cast<uint4*>(srow + (unit << 4)) =
+                make_uint4(dk[c][u * 4], dk[c][u * 4 + 1], dk[c][u * 4 + 2], dk[c][u * 4 + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        // deferred by one iteration: what the previous MMA 2 produced leaves while this one runs
+        if (it > 0) {
+          reduce_dq((it - 1) & 1, pb, ph, pqt);
+          tc_fence_before();
+          mbar_arrive(&bar_dqfree[(it - 1) & 1]);
+          if (pend_kv) {
+            store_kv_row(kv_b, kv_h, kv_kb);
+            tc_fence_before();
+            mbar_arrive(bar_kvdone);
+            pend_kv = false;
+          }
+        }
+        pb = b; ph = h; pqt = qt;
+        if (qt == nqt - 1) {
+          pend_kv = true;
+          kv_b = b; kv_h = h; kv_kb = kb;
+        }
+      }
+    }
+    if (it > 0) {
+      mbar_wait(bar_m2, (it - 1) & 1);
+      tc_fence_after();
+      reduce_dq((it - 1) & 1, pb, ph, pqt);
+      if (pend_kv) store_kv_row(kv_b, kv_h, kv_kb);
+    }
+    if (stg_pending && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// dqkv[b, n, 0, h, :] = bf16(dq32[b, n, h, :]) — the query-gradient slot, after the reduce-adds
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long long rows, int hd) {
+  pdl_wait();
+  const int vec = hd >> 3;
+  const long long total = rows * vec;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / vec;
+    const int c = static_cast<int>(i - row * vec) << 3;
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(dq32 + row * hd + c));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(dq32 + row * hd + c) + 1);
+    uint4 w;
+    w.x = pack_bf16(a.x, a.y);
+    w.y = pack_bf16(a.z, a.w);
+    w.z = pack_bf16(b.x, b.y);
+    w.w = pack_bf16(b.z, b.w);
+    *reinterpret_cast<uint4*>(dqkv + row * 3 * hd + c) = w;
+  }
+}
+
+int64_t attention_tc_bwd_long_workspace(int64_t batch, int64_t tokens, int64_t heads) {
+  return batch * tokens * heads * 64 * static_cast<int64_t>(sizeof(float));
+}
+
+int attention_tc_bwd_long(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                          void* workspace, int64_t batch, int64_t tokens, int64_t heads, float scale,
+                          cudaStream_t stream) {
+  AttnLongBwdParams p;
+  p.N = static_cast<int>(tokens);
+  p.H = static_cast<int>(heads);
+  p.kw = static_cast<int>((tokens + 15) / 16 * 16);
+  p.nkb = (p.kw + 127) / 128;
+  p.nqt = (p.N + 127) / 128;
+  p.items = static_cast<int>(batch * heads * p.nkb);
+  p.scale = scale;
+  p.lse = lse;
+  p.delta = delta;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  const int64_t hd = heads * 64;
+  float* dq32 = reinterpret_cast<float*>(workspace);
+  FV_CHECK_CUDA(cudaMemsetAsync(dq32, 0, attention_tc_bwd_long_workspace(batch, tokens, heads), stream));
+  CUtensorMap mq, mdo, mdq;
+  int rc = make_tok_map(&mq, qkv, batch, tokens, 3 * hd);
+  if (rc != FV_OK) return rc;
+  rc = make_tok_map(&mdo, dout, batch, tokens, hd);
+  if (rc != FV_OK) return rc;
+  {  // fp32 scratch [B, N, H*64]: box = 32 columns (128 B) x 32 tokens x 1 image, 128B swizzle
+    EncodeTiledFn enc = get_encode_tiled();
+    FV_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(hd), static_cast<cuuint64_t>(tokens), static_cast<cuuint64_t>(batch)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(hd) * 4, static_cast<cuuint64_t>(hd) * tokens * 4};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&mdq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dq32, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(dq scratch) failed (%d)", static_cast<int>(r));
+      return FV_ERR_CUDA;
+    }
+  }
+  const int smem = 12 * ATB_TILE + 8 * 4096 + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    FV_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  FV_CHECK_CUDA(fv::launch_pdl(attn_tc_bwd_long_kernel, dim3(static_cast<unsigned>(grid)), dim3(ATLB_THREADS), smem, stream,
+                               mq, mdo, mdq, p));
+  FV_LAUNCH_CHECK();
+  const long long rows = batch * tokens;
+  const long long total = rows * (hd / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  FV_CHECK_CUDA(fv::launch_pdl(attn_dq_convert_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream,
+                               static_cast<const float*>(dq32), p.dqkv, rows, static_cast<int>(hd)));
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
 }  // namespace fv

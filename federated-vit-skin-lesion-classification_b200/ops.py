@@ -284,8 +284,10 @@ def attention_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, batch: in
         raise FedVitError("attention_bwd: dout must be contiguous bf16")
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
+    ws_bytes = int(LIB.raw("fv_attention_bwd_workspace")(batch, tokens, heads))
+    ws = torch.empty(ws_bytes, device=qkv.device, dtype=torch.uint8) if ws_bytes else None
     LIB.call("fv_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-             delta.data_ptr(), dqkv.data_ptr(), BF16, batch, tokens, heads, scale, _stream(qkv))
+             delta.data_ptr(), dqkv.data_ptr(), BF16, batch, tokens, heads, scale, _ptr(ws), ws_bytes, _stream(qkv))
     return dqkv
 
 

@@ -136,13 +136,17 @@ int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* 
  *   lse : fp32 [B, H, N] log-sum-exp of the scaled scores, saved for the backward
  * Backward writes dqkv in the same [B, N, 3, H, 64] layout.
  *   delta: fp32 [B, H, N] scratch (rowsum(dO * O)), caller-owned.
+ *   workspace: caller-owned scratch of fv_attention_bwd_workspace(batch, tokens, heads) bytes, 128-byte
+ *     aligned (0 bytes / NULL for tokens <= 256 and > 768; the long-sequence tcgen05 path accumulates
+ *     the query gradient there in fp32 with TMA reduce-adds before converting it into dqkv).
  * head_dim is 64 for every ViT the path covers (Tiny/Base/Large).
  * ---------------------------------------------------------------------------------------- */
 int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtype,
                      int64_t batch, int64_t tokens, int64_t heads, float scale, void* stream);
+int64_t fv_attention_bwd_workspace(int64_t batch, int64_t tokens, int64_t heads);
 int fv_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
-                     float* delta, void* dqkv, int dtype,
-                     int64_t batch, int64_t tokens, int64_t heads, float scale, void* stream);
+                     float* delta, void* dqkv, int dtype, int64_t batch, int64_t tokens,
+                     int64_t heads, float scale, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Patch embedding helpers (timm PatchEmbed.proj = Conv2d(C,D,16,16) + cls/pos, model.py:193).
