@@ -192,9 +192,14 @@ def run_gpu_arm(args) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version / debug lines to stdout by default: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL (and anything else native) may write its version / debug lines to file descriptor 1:
+        # point fd 1 at stderr for the duration of the run and restore it for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
+    else:
+        saved_stdout = None
 
     cfg = model_config()
     utils.seed_everything(42)
@@ -343,7 +348,12 @@ def run_gpu_arm(args) -> None:
                 "value": ips, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": "2 timed train steps (after 1 warm-up) of 16 images, fp32, ViT-B/16 224 — oracle/ CPU port "
                           "of the reference path on this box's host cores"}
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        if saved_stdout is not None:
+            os.dup2(2, 1)  # teardown chatter goes to stderr again
     if world > 1:
         dist.destroy_process_group()
 

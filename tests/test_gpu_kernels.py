@@ -162,7 +162,9 @@ def test_layernorm_fwd_bwd(cols):
     assert rel_err(dxb, xr.grad) < 1e-2
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (1, 577, 2), (3, 64, 1), (2, 65, 2), (1, 1, 1)])
+@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (3, 64, 1), (2, 65, 2), (1, 1, 1), (2, 256, 2),   # one-tile tcgen05 kernels
+                                   (1, 577, 2), (3, 257, 2), (5, 400, 3), (2, 768, 1),           # long-sequence tcgen05 kernels
+                                   (1, 800, 1)])                                                 # mma.sync flash kernels
 def test_flash_attention_fwd_bwd(B, N, H):
     g = _gen(N)
     qkv = torch.randn(B * N, 3 * H * 64, device=DEV, generator=g).bfloat16()
@@ -181,8 +183,14 @@ def test_flash_attention_fwd_bwd(B, N, H):
     for i, name in enumerate("qkv"):
         err = float((dqkv[:, i].double().cpu() - ref[:, i].cpu()).norm())
         assert err < 1e-2 * max(float(ref[:, i].norm()), 1e-3 * scale_ref), name
-    # bit-reproducible (no atomics on the attention path)
-    assert torch.equal(ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).view(B * N, 3, H * 64).float(), dqkv)
+    # reproducible: no atomics on the attention path, except that the long-sequence kernel sums the
+    # key blocks' dQ contributions with fp32 TMA reduce-adds (order-dependent in the last fp32 bits)
+    again = ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).view(B * N, 3, H * 64).float()
+    assert torch.equal(again[:, 1:], dqkv[:, 1:])
+    if 256 < N <= 768:
+        assert rel_err(again[:, 0], dqkv[:, 0]) < 1e-2
+    else:
+        assert torch.equal(again[:, 0], dqkv[:, 0])
 
 
 def _asl_ref(logits, targets, gn=4.0, gp=1.0, clip=0.05, eps=1e-8):
