@@ -351,7 +351,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   uint64_t* bar_dqfree = bars + 11;
   uint64_t* bar_aux = bars + 12;                // [ATB_AUX] lse / delta of item n ready in sAux[n % ATB_AUX]
   uint64_t* bar_auxfree = bar_aux + ATB_AUX;    // [ATB_AUX] ... and read for the last time
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_auxfree + ATB_AUX);
+  uint64_t* bar_c = bar_auxfree + ATB_AUX;      // S / dP are in the math warps' registers: TMEM may be rewritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_c + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (p.N + 127) >> 7;  // query tiles == key blocks (1 or 2)
@@ -368,6 +369,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     mbar_init(bar_m2, 1);
     mbar_init(bar_kvfree, 256);
     mbar_init(bar_dqfree, 256);
+    mbar_init(bar_c, 256);
     for (int i = 0; i < ATB_AUX; ++i) {
       mbar_init(&bar_aux[i], 64);
       mbar_init(&bar_auxfree[i], 256);
@@ -464,9 +466,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         for (int qt = 0; qt < nt; ++qt, ++it) {
           const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQ + qt * ATB_TILE), ATB_TILE, 1024);
           const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sdO + qt * ATB_TILE), ATB_TILE, 1024);
-          mbar_wait(bar_p, it & 1);  // P / dS tiles written, S / dP consumed
+          // the next (key block, query tile)'s scores are issued as soon as this one's S / dP have
+          // been read into registers (bar_c) — half the softmax math and the P / dS stores earlier
+          // than "P / dS written" (bar_p); ncu had the math warps waiting on bar_s for a third of
+          // their time
+          mbar_wait(bar_c, it & 1);
           tc_fence_after();
-          // the next (key block, query tile)'s scores go first so its softmax math overlaps this MMA 2
           if (qt + 1 < nt) {
             if (kb == 0) mbar_wait(&bar_ld[1], ph);
             tc_fence_after();
@@ -476,6 +481,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
             tc_fence_after();
             issue_mma1(kb + 1, 0);
           }
+          mbar_wait(bar_p, it & 1);  // P / dS tiles written
+          tc_fence_after();
           if (qt == 0 && kvn > 0) mbar_wait(bar_kvfree, (kvn - 1) & 1);  // previous dK / dV have left TMEM
           if (kb == 0 && qt == 0 && n > 0) mbar_wait(bar_dqfree, (n - 1) & 1);  // previous item's dQ likewise
           tc_fence_after();
@@ -636,6 +643,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           tc_fence_after();
           uint32_t pk[2][16], dk[2][16];
           const bool rows_live = qt * 128 + quarter * 32 < p.N;  // warp-uniform
+          bool consumed = false;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             // 32-key chunks are dealt out alternately (group 0: chunks 0 and 2, group 1: 1 and 3) so a
@@ -651,6 +659,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
             tmem_ld_32x32(lane_base + T_S + ch * 32, s);
             tmem_ld_32x32(lane_base + T_DP + ch * 32, d);
             tmem_ld_wait();
+            if (c == 1) {  // this thread's last read of S / dP
+              tc_fence_before();
+              mbar_arrive(bar_c);
+              consumed = true;
+            }
             if (key0 + 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
               const float dls = dl * p.scale;
 #pragma unroll
@@ -678,6 +691,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
                 dk[c][i >> 1] = pack_bf16(s0, s1);
               }
             }
+          }
+          if (!consumed) {  // second chunk skipped (padding): nothing left to read
+            tc_fence_before();
+            mbar_arrive(bar_c);
           }
           if (it > 0) {
             mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 retired: sP / sdS free, its dK / dV / dQ final
@@ -1097,7 +1114,8 @@ attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   uint64_t* bar_m2 = bars + 10;
   uint64_t* bar_dqfree = bars + 11;  // [2] dQ TMEM buffer drained
   uint64_t* bar_kvdone = bars + 13;  // dK / dV of the finished item drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bar_c = bars + 14;       // S / dP are in the math warps' registers: TMEM may be rewritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hd = p.H * 64;
@@ -1118,6 +1136,7 @@ attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     mbar_init(bar_p, 256);
     mbar_init(bar_m2, 1);
     mbar_init(bar_kvdone, 256);
+    mbar_init(bar_c, 256);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -1209,9 +1228,9 @@ attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         const int slot = it & 1;
         const uint64_t dQ_mn = make_smem_desc_sw128(smem_u32(sQD + slot * 2 * ATB_TILE), ATB_TILE, 1024);
         const uint64_t dO_mn = make_smem_desc_sw128(smem_u32(sQD + slot * 2 * ATB_TILE + ATB_TILE), ATB_TILE, 1024);
-        mbar_wait(bar_p, it & 1);  // P / dS tiles written, S / dP consumed
+        // the next iteration's scores are issued as soon as this one's S / dP are in registers
+        mbar_wait(bar_c, it & 1);
         tc_fence_after();
-        // the next iteration's scores go first so its softmax math overlaps this MMA 2
         if (qt + 1 < nqt) {
           mbar_wait(&bar_qd[(it + 1) & 1], ((it + 1) >> 1) & 1);
           tc_fence_after();
@@ -1224,6 +1243,8 @@ attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           tc_fence_after();
           issue_mma1((n + 1) & 1, (it + 1) & 1, kwb_of(kb2));
         }
+        mbar_wait(bar_p, it & 1);  // P / dS tiles written
+        tc_fence_after();
         if (qt == 0 && n > 0) mbar_wait(bar_kvdone, (n - 1) & 1);  // previous item's dK / dV have left TMEM
         if (it >= 2) mbar_wait(&bar_dqfree[it & 1], ((it >> 1) - 1) & 1);  // dQ buffer of iteration it-2 drained
         tc_fence_after();
@@ -1321,6 +1342,7 @@ attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         tc_fence_after();
         uint32_t pk[2][16], dk[2][16];
         const bool rows_live = qt * 128 + quarter * 32 < p.N;  // warp-uniform
+        bool consumed = false;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int ch = 2 * c + hf;  // 32-key chunks dealt alternately to the two groups
@@ -1334,6 +1356,11 @@ attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           tmem_ld_32x32(lane_base + T_S + ch * 32, s);
           tmem_ld_32x32(lane_base + T_DP + ch * 32, d);
           tmem_ld_wait();
+          if (c == 1) {  // this thread's last read of S / dP
+            tc_fence_before();
+            mbar_arrive(bar_c);
+            consumed = true;
+          }
           if (key0 + 32 <= p.N) {
             const float dls = dl * p.scale;
 #pragma unroll
@@ -1361,6 +1388,10 @@ attn_tc_bwd_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
               dk[c][i >> 1] = pack_bf16(s0, s1);
             }
           }
+        }
+        if (!consumed) {  // second chunk skipped (padding): nothing left to read
+          tc_fence_before();
+          mbar_arrive(bar_c);
         }
         if (it > 0) {
           mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 retired: sP / sdS free, its dQ / dK / dV final

@@ -2,7 +2,7 @@
 for it (EMA, clip_grad_norm, WarmupCosineScheduler, seed_everything, get_device, load_config,
 checkpoint save/load), re-implemented over the flat arena.
 
-Out of scope here: TTA evaluation, auto batch-size probing, the
+Out of scope here: auto batch-size probing, the
 sklearn metric tables — they are host-side data/driver code, not the hot path.
 """
 from __future__ import annotations
@@ -271,3 +271,84 @@ class MixupCutmix:
 def mixup_criterion(criterion, logits, labels_a, labels_b, lam):
     """Reference utils.py:167-168."""
     return lam * criterion(logits, labels_a) + (1 - lam) * criterion(logits, labels_b)
+
+
+# ================================================================================================
+# evaluation, plain and with test-time augmentation (scope row f4, first half) — reference
+# utils.py:200-280, same names / signatures / returned keys
+# ================================================================================================
+@torch.no_grad()
+def evaluate_with_tta(model: nn.Module, loader, device: torch.device, use_metadata: bool = True,
+                      use_amp: bool = True):
+    """TTA: the loader yields ``images`` of shape (B, T, C, H, W) (T augmented views, built on the
+    host); the views run as ONE forward of batch B*T on the sm_100a kernels and their logits are
+    averaged (reference utils.py:200-230). Returns (preds, labels, logits[B_total, C])."""
+    model.eval()
+    all_preds, all_labels, all_logits = [], [], []
+    for batch in loader:
+        images = batch["images"]
+        labels = batch["label"]
+        B, T = images.shape[:2]
+        flat = images.reshape(-1, *images.shape[2:]).to(device, non_blocking=True)
+        meta = None
+        if use_metadata and "metadata" in batch:
+            meta = batch["metadata"].to(device, non_blocking=True)
+            meta = meta.unsqueeze(1).expand(-1, T, -1).reshape(B * T, -1)
+        with torch.amp.autocast(device_type=device.type, enabled=use_amp and device.type == "cuda",
+                                dtype=torch.bfloat16):
+            logits_flat = model(flat, metadata=meta)["logits"]
+        logits = logits_flat.float().view(B, T, -1).mean(dim=1)
+        all_preds.extend(logits.argmax(dim=1).cpu().tolist())
+        all_labels.extend(torch.as_tensor(labels).tolist())
+        all_logits.append(logits.cpu().numpy())
+    return all_preds, all_labels, np.concatenate(all_logits, axis=0)
+
+
+@torch.no_grad()
+def evaluate(model: nn.Module, loader, device: torch.device, use_metadata: bool = True, use_amp: bool = True) -> Dict:
+    """Standard (no-TTA) evaluation with the fused cross-entropy kernel (reference utils.py:237-280):
+    loss, accuracy, balanced accuracy, macro-F1, confusion matrix, per-class recall, predictions."""
+    model.eval()
+    loss_sum = torch.zeros((), device=device, dtype=torch.float32)
+    preds, gold = [], []
+    num_classes = None
+    for batch in loader:
+        images = batch["image"].to(device, non_blocking=True)
+        labels = batch["label"].to(device, non_blocking=True)
+        meta = batch.get("metadata")
+        if meta is not None:
+            meta = meta.to(device, non_blocking=True)
+        with torch.amp.autocast(device_type=device.type, enabled=use_amp and device.type == "cuda",
+                                dtype=torch.bfloat16):
+            logits = model(images, metadata=meta if use_metadata else None)["logits"]
+        loss, _ = ops.ce_loss(logits.float().contiguous(), labels)
+        loss_sum += loss.reshape(()) * images.size(0)
+        num_classes = logits.shape[1]
+        preds.append(logits.argmax(1))
+        gold.append(labels)
+    p = torch.cat(preds).cpu().numpy() if preds else np.zeros(0, np.int64)
+    y = torch.cat(gold).cpu().numpy() if gold else np.zeros(0, np.int64)
+    total = max(len(y), 1)
+    nc = int(num_classes or 1)
+    cm = np.zeros((nc, nc), dtype=np.int64)
+    np.add.at(cm, (y, p), 1)
+    support = cm.sum(1)
+    recall = [float(cm[i, i] / support[i]) if support[i] > 0 else 0.0 for i in range(nc)]
+    present = support > 0
+    tp = np.diag(cm).astype(np.float64)
+    predicted = cm.sum(0).astype(np.float64)
+    prec = np.divide(tp, predicted, out=np.zeros_like(tp), where=predicted > 0)
+    rec = np.divide(tp, support.astype(np.float64), out=np.zeros_like(tp), where=present)
+    den = prec + rec
+    f1 = np.divide(2 * prec * rec, den, out=np.zeros_like(tp), where=den > 0)
+    return {
+        "loss": float(loss_sum.item()) / total,
+        "accuracy": float(tp.sum() / total),
+        "balanced_accuracy": float(rec[present].mean()) if present.any() else 0.0,
+        # sklearn f1_score(average="macro", zero_division=0): mean over the labels seen in y or p
+        "macro_f1": float(f1[present | (predicted > 0)].mean()) if (present | (predicted > 0)).any() else 0.0,
+        "confusion_matrix": cm,
+        "per_class_recall": recall,
+        "all_preds": p.tolist(),
+        "all_labels": y.tolist(),
+    }

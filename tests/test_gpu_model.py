@@ -540,3 +540,32 @@ def test_train_one_epoch_with_mixup_cutmix_runs_reference_wiring():
 
     plain, mixed = epoch(0.0, 0.0), epoch(0.4, 0.5)
     assert np.isfinite(plain) and np.isfinite(mixed) and plain != mixed
+
+
+@pytest.mark.gpu
+def test_evaluate_and_tta_match_reference_semantics():
+    """utils.evaluate / utils.evaluate_with_tta (reference utils.py:200-280): metrics agree with
+    sklearn on the same predictions; the TTA logits are the mean over the views of the per-view logits."""
+    from sklearn.metrics import balanced_accuracy_score, confusion_matrix, f1_score
+
+    cfg = micro_config()
+    utils.seed_everything(3)
+    m = model.build_model(cfg).to(DEV).eval()
+    g = torch.Generator().manual_seed(4)
+    batches = [{"image": torch.randn(8, 3, 32, 32, generator=g), "label": torch.randint(0, 7, (8,), generator=g)}
+               for _ in range(3)]
+    out = utils.evaluate(m, batches, DEV, use_metadata=False, use_amp=False)
+    y, p = out["all_labels"], out["all_preds"]
+    assert out["balanced_accuracy"] == pytest.approx(balanced_accuracy_score(y, p))
+    assert out["macro_f1"] == pytest.approx(f1_score(y, p, average="macro", zero_division=0))
+    assert np.array_equal(out["confusion_matrix"], confusion_matrix(y, p, labels=list(range(7))))
+    with torch.no_grad():
+        want_loss = sum(float(torch.nn.functional.cross_entropy(m(b["image"].to(DEV))["logits"], b["label"].to(DEV))) * 8
+                        for b in batches) / 24
+    assert out["loss"] == pytest.approx(want_loss, rel=1e-5)
+    views = torch.randn(4, 5, 3, 32, 32, generator=g)
+    preds, labels, logits = utils.evaluate_with_tta(m, [{"images": views, "label": torch.tensor([0, 1, 2, 3])}], DEV,
+                                                    use_metadata=False, use_amp=False)
+    with torch.no_grad():
+        per_view = m(views.view(-1, 3, 32, 32).to(DEV))["logits"].view(4, 5, -1).mean(1)
+    assert rel_err(torch.from_numpy(logits), per_view) < 1e-6 and preds == per_view.argmax(1).tolist() and labels == [0, 1, 2, 3]
