@@ -69,12 +69,17 @@ def main() -> None:
         for i in range(3):
             step(i)
         torch.cuda.synchronize()
+        import time
+
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
+        c0 = time.perf_counter()
         for i in range(steps):
             step(i)
+        cpu_ms = (time.perf_counter() - c0) * 1e3 / steps  # host time to ENQUEUE a step (no sync inside)
         t1.record()
         torch.cuda.synchronize()
+        print(f"  host enqueue time {cpu_ms:6.2f} ms/step (GPU step time below: the host has to stay under it)")
         return t0.elapsed_time(t1) / steps
 
     for rep in range(2):
