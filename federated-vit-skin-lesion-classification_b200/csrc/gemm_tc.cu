@@ -1075,7 +1075,12 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     configured = true;
   }
   const int total = p.num_m_blocks * p.num_n_blocks * p.split_k;
-  const int grid = total < num_sms() ? total : num_sms();
+  int grid = total < num_sms() ? total : num_sms();
+  // FEDVIT_GEMM_GRID (measurement switch, read per call): cap on the CTAs (= SMs) of this kernel
+  if (const char* e = getenv("FEDVIT_GEMM_GRID")) {
+    const int v = atoi(e);
+    if (v > 0 && v < grid) grid = v;
+  }
   FV_CHECK_CUDA(fv::launch_pdl(gemm_tc_kernel<EPI, BF16>, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, stream, ta, tb, tc, tx, p));
   FV_LAUNCH_CHECK();
   return FV_OK;

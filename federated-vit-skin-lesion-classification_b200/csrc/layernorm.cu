@@ -365,6 +365,185 @@ layernorm_bwd_pipe_kernel(const void* __restrict__ dy, const float* __restrict__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy ring variant (bf16 dy + residual gradient, cols a multiple of 128): one CTA per SM.
+// A producer warp streams whole rows — x, the residual gradient and dy, 10 * cols bytes — into a
+// shared-memory ring with cp.async.bulk (1-D TMA copies, one mbarrier per group of eight rows);
+// eight consumer warps take one row of the group each, pull it into registers, hand the slot back
+// and do the arithmetic. With the ring holding 16 - 56 rows per SM (~180 KB in flight instead of
+// the ~60 KB eight register-staged rows give) an SM no longer needs 147 peers to cover the HBM
+// latency: a fraction of the SMs saturates the memory system, which is what lets this pass share
+// the GPU with a tensor-bound kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int LNR_ROWS = 8;                          // consumer warps == rows per group
+constexpr int LNR_THREADS = (LNR_ROWS + 1) * 32;     // + the producer warp
+constexpr int LNR_MAX_DEPTH = 8;
+constexpr int LNR_SM_NUM = 73, LNR_SM_DEN = 100;  // share of the SMs the ring kernel runs on (108 of 148)
+
+__device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NVW /* float4 per lane: cols == 128 * NVW */>
+__global__ void __launch_bounds__(LNR_THREADS, 1)
+layernorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                          const float* __restrict__ gamma, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ dres,
+                          float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_lp,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
+                          const float* __restrict__ lp_scale, int rows_per_scale, int depth) {
+  constexpr int COLS = NVW * 128;
+  constexpr uint32_t X_BYTES = COLS * 4, D_BYTES = COLS * 2;
+  constexpr uint32_t ROW_BYTES = 2 * X_BYTES + D_BYTES;
+  constexpr uint32_t GROUP_BYTES = LNR_ROWS * ROW_BYTES;
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  uint8_t* ring = ring_raw + ((128u - (smem_u32(ring_raw) & 127u)) & 127u);
+  __shared__ uint64_t full_bar[LNR_MAX_DEPTH], empty_bar[LNR_MAX_DEPTH];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < depth; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], LNR_ROWS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  const long long groups = (rows + LNR_ROWS - 1) / LNR_ROWS;
+
+  if (warp == LNR_ROWS) {
+    // ------------------------------- producer ------------------------------------------------
+    int slot = 0;
+    uint32_t phase = 0;
+    const int r = lane / 3, which = lane - 3 * r;  // lanes 0..23: (row of the group, which array)
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+      mbar_wait(&empty_bar[slot], phase ^ 1);
+      const long long row0 = g * LNR_ROWS;
+      const int nrows = rows - row0 < LNR_ROWS ? static_cast<int>(rows - row0) : LNR_ROWS;
+      if (lane == 0) mbar_expect_tx(&full_bar[slot], nrows * ROW_BYTES);
+      __syncwarp();
+      if (lane < 3 * LNR_ROWS && r < nrows) {
+        uint8_t* dst = ring + slot * GROUP_BYTES + r * ROW_BYTES;
+        const long long row = row0 + r;
+        if (which == 0) bulk_load_row(dst, x + row * COLS, X_BYTES, &full_bar[slot]);
+        else if (which == 1) bulk_load_row(dst + X_BYTES, dres + row * COLS, X_BYTES, &full_bar[slot]);
+        else bulk_load_row(dst + 2 * X_BYTES, dy + row * COLS, D_BYTES, &full_bar[slot]);
+      }
+      if (++slot == depth) { slot = 0; phase ^= 1; }
+    }
+    return;
+  }
+
+  // --------------------------------- consumers -----------------------------------------------
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  // gamma lives in registers while the budget allows (168 per thread at 288 threads); wider rows
+  // re-read it through L1 each row
+  constexpr bool GM_REGS = NVW <= 5;
+  float4 gm[GM_REGS ? NVW : 1], dg[NVW], db[NVW];
+#pragma unroll
+  for (int i = 0; i < NVW; ++i) {
+    if (GM_REGS) gm[i] = __ldg(g4 + i * 32 + lane);
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  constexpr float inv_cols = 1.0f / COLS;
+  int slot = 0;
+  uint32_t phase = 0;
+  long long row = static_cast<long long>(blockIdx.x) * LNR_ROWS + warp;
+  const long long stride = static_cast<long long>(gridDim.x) * LNR_ROWS;
+  float mu_n = 0.f, rs_n = 0.f, lps_n = 1.f;
+  if (row < rows) {
+    mu_n = __ldg(mean + row);
+    rs_n = __ldg(rstd + row);
+    if (lp_scale != nullptr) lps_n = __ldg(lp_scale + row / rows_per_scale);
+  }
+  for (long long g = blockIdx.x; g < groups; g += gridDim.x, row += stride) {
+    const bool live = row < rows;
+    const float mu = mu_n, rs = rs_n, lps = lps_n;
+    if (row + stride < rows) {  // the next row's statistics travel while this one is processed
+      mu_n = __ldg(mean + row + stride);
+      rs_n = __ldg(rstd + row + stride);
+      if (lp_scale != nullptr) lps_n = __ldg(lp_scale + (row + stride) / rows_per_scale);
+    }
+    mbar_wait(&full_bar[slot], phase);
+    float4 xh[NVW], rr[NVW];
+    uint2 dd[NVW];
+    if (live) {
+      const uint8_t* base = ring + slot * GROUP_BYTES + warp * ROW_BYTES;
+#pragma unroll
+      for (int i = 0; i < NVW; ++i) {
+        xh[i] = *reinterpret_cast<const float4*>(base + (i * 32 + lane) * 16);
+        rr[i] = *reinterpret_cast<const float4*>(base + X_BYTES + (i * 32 + lane) * 16);
+        dd[i] = *reinterpret_cast<const uint2*>(base + 2 * X_BYTES + (i * 32 + lane) * 8);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);  // the row is in registers: the slot can be refilled
+    if (++slot == depth) { slot = 0; phase ^= 1; }
+    if (!live) continue;
+    float4 gy[NVW];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVW; ++i) {
+      const float2 lo = unpack_bf16(dd[i].x), hi = unpack_bf16(dd[i].y);
+      const float4 d = make_float4(lo.x, lo.y, hi.x, hi.y);
+      const float4 xv = xh[i];
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      const float4 g = GM_REGS ? gm[GM_REGS ? i : 0] : __ldg(g4 + i * 32 + lane);
+      gy[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y;
+      dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+      s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+    }
+    s1 = warp_sum(s1) * inv_cols;
+    s2 = warp_sum(s2) * inv_cols;
+    float4* orow = reinterpret_cast<float4*>(dx + row * COLS);
+    uint2* lrow = reinterpret_cast<uint2*>(dx_lp + row * COLS);
+#pragma unroll
+    for (int i = 0; i < NVW; ++i) {
+      float4 o;
+      o.x = rs * (gy[i].x - s1 - xh[i].x * s2) + rr[i].x;
+      o.y = rs * (gy[i].y - s1 - xh[i].y * s2) + rr[i].y;
+      o.z = rs * (gy[i].z - s1 - xh[i].z * s2) + rr[i].z;
+      o.w = rs * (gy[i].w - s1 - xh[i].w * s2) + rr[i].w;
+      orow[i * 32 + lane] = o;
+      if (dx_lp != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16(o.x * lps, o.y * lps);
+        pk.y = pack_bf16(o.z * lps, o.w * lps);
+        lrow[i * 32 + lane] = pk;
+      }
+    }
+  }
+  // dgamma / dbeta: the eight warps' register partials meet in the (now idle) ring
+  asm volatile("bar.sync 1, %0;" ::"n"(LNR_ROWS * 32) : "memory");
+  float* red_g = reinterpret_cast<float*>(ring);
+  float* red_b = red_g + LNR_ROWS * COLS;
+#pragma unroll
+  for (int i = 0; i < NVW; ++i) {
+    reinterpret_cast<float4*>(red_g + warp * COLS)[i * 32 + lane] = dg[i];
+    reinterpret_cast<float4*>(red_b + warp * COLS)[i * 32 + lane] = db[i];
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(LNR_ROWS * 32) : "memory");
+  for (int c = threadIdx.x; c < COLS; c += LNR_ROWS * 32) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < LNR_ROWS; ++w) {
+      sg += red_g[w * COLS + c];
+      sb += red_b[w * COLS + c];
+    }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
 }  // namespace fv
 
 extern "C" int fv_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y,
@@ -412,21 +591,75 @@ extern "C" int fv_layernorm_bwd(const void* dy, int dy_dtype, const float* x, co
                "fv_layernorm_bwd: lp_row_scale needs dx_lp and rows_per_scale > 0");
   if (rows == 0) return FV_OK;
   static int minb = -1;
-  if (minb < 0) {
-    // 0 (default): software-pipelined kernel, two CTAs/SM (5.65 TB/s alone, 86 % of the measured
-    // copy bandwidth); 3 / 2: one row per pair at a time with three / two CTAs/SM (5.26 TB/s) — A/B switch
+  if (minb < 0 || getenv("FEDVIT_LN_REREAD") != nullptr) {
+    // FEDVIT_LN_MINB (A/B switch). Default: the bulk-copy ring kernel wherever it applies (bf16 dy with a
+    // residual gradient, cols % 128 == 0: 107 us for 50432 x 768 on 100 SMs = 5.8 TB/s, 0.89 of the measured
+    // copy bandwidth), else the software-pipelined kernel. 0: pipelined kernel everywhere (131 us, 0.72);
+    // 3 / 2: one row per warp pair at a time with three / two CTAs/SM.
     const char* e = getenv("FEDVIT_LN_MINB");
-    minb = e ? atoi(e) : 0;
+    minb = e ? atoi(e) : 9;
   }
-  int64_t want = ceil_div(rows, LNB_ROWS);
-  const int64_t cap = static_cast<int64_t>(num_sms()) * (minb == 0 ? 2 : minb);
-  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-  const size_t smem = 2 * LNB_ROWS * cols * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(dx_lp);
+  // FEDVIT_LN_GRID (measurement switch, read per call): cap on the number of SMs this pass may use
+  int sm_cap = num_sms();
+  bool capped = false;
+  if (const char* e = getenv("FEDVIT_LN_GRID")) {
+    const int v = atoi(e);
+    if (v > 0 && v < sm_cap) {
+      sm_cap = v;
+      capped = true;
+    }
+  }
+  const bool ring_ok = dy_dtype == FV_BF16 && dres != nullptr && cols % 128 == 0 && cols <= 1024 &&
+                       ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
+                         reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
+  if (minb == 9 && ring_ok) {
+    // bulk-copy ring kernel: as many 8-row groups as fit beside the static barriers
+    const size_t group = static_cast<size_t>(LNR_ROWS) * 10 * cols;
+    int depth = static_cast<int>((220 * 1024) / group);
+    if (depth > LNR_MAX_DEPTH) depth = LNR_MAX_DEPTH;
+    const size_t smem_ring = depth * group + 128;
+    const int64_t groups = ceil_div(rows, LNR_ROWS);
+    // ~180 KB in flight per SM saturates HBM from about 100 SMs; more CTAs only add DRAM page
+    // conflicts (measured for 50432 x 768: 96 - 120 SMs 105 - 108 us, 148: 107 - 113, 80: 116, 56: 154)
+    if (!capped) sm_cap = (sm_cap * LNR_SM_NUM) / LNR_SM_DEN;
+    if (sm_cap < 1) sm_cap = 1;
+    const unsigned grid_r = static_cast<unsigned>(groups < sm_cap ? groups : sm_cap);
+    const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+#define FV_LN_RING(NVW)                                                                                      \
+  do {                                                                                                       \
+    static bool configured = false;                                                                          \
+    if (!configured) {                                                                                       \
+      FV_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_ring_kernel<NVW>,                                     \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));          \
+      configured = true;                                                                                     \
+    }                                                                                                        \
+    FV_CHECK_CUDA(fv::launch_pdl(layernorm_bwd_ring_kernel<NVW>, dim3(grid_r), dim3(LNR_THREADS), smem_ring, \
+                                 st, dyb, x, gamma, mean, rstd, dres, dx, lp, dgamma, dbeta,                 \
+                                 static_cast<long long>(rows), lp_row_scale, (int)rows_per_scale, depth));   \
+  } while (0)
+    switch (cols / 128) {
+      case 1: FV_LN_RING(1); break;
+      case 2: FV_LN_RING(2); break;
+      case 3: FV_LN_RING(3); break;
+      case 4: FV_LN_RING(4); break;
+      case 5: FV_LN_RING(5); break;
+      case 6: FV_LN_RING(6); break;
+      case 7: FV_LN_RING(7); break;
+      default: FV_LN_RING(8); break;
+    }
+#undef FV_LN_RING
+    FV_LAUNCH_CHECK();
+    return FV_OK;
+  }
+  int64_t want = ceil_div(rows, LNB_ROWS);
+  const int64_t cap = static_cast<int64_t>(sm_cap) * (minb == 0 || minb == 9 ? 2 : minb);
+  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+  const size_t smem = 2 * LNB_ROWS * cols * sizeof(float);
 #define FV_LN_BWD(NV, BF)                                                                        \
   do {                                                                                           \
-    if (minb == 0)                                                                               \
+    if (minb == 0 || minb == 9)                                                                  \
       FV_CHECK_CUDA(fv::launch_pdl(layernorm_bwd_pipe_kernel<NV, BF>, dim3(grid), dim3(LNB_THREADS), smem, st, dy, x, gamma, mean, rstd, dres, dx, \
                                    lp, dgamma, dbeta, rows, (int)cols, lp_row_scale, (int)rows_per_scale)); \
     else if (minb == 2)                                                                          \

@@ -163,6 +163,45 @@ def test_layernorm_fwd_bwd(cols):
     assert rel_err(dxb, xr.grad) < 1e-2
 
 
+@pytest.mark.parametrize("cols", [128, 384, 768, 1024])
+@pytest.mark.parametrize("rows", [5, 1031, 8 * 148 * 3 + 1])
+def test_layernorm_bwd_ring_kernel(rows, cols, monkeypatch):
+    """The bulk-copy ring kernel (default for bf16 dy + residual gradient, cols % 128 == 0) against an
+    fp64 reference and against the register-pipelined kernel: ragged last group, fewer rows than one
+    group, more groups than the ring is deep, the stochastic-depth factor on the bf16 copy, capped grids."""
+    g = _gen(rows + cols)
+    x = torch.randn(rows, cols, device=DEV, generator=g) * 2 + 0.5
+    gam = torch.randn(cols, device=DEV, generator=g)
+    dy = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    dres = torch.randn(rows, cols, device=DEV, generator=g)
+    xr, gr = x.double().requires_grad_(True), gam.double().requires_grad_(True)
+    br = torch.zeros(cols, device=DEV, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.layer_norm(xr, (cols,), gr, br, 1e-6).backward(dy.double())
+    mean = x.double().mean(1).float()
+    rstd = (x.double().var(1, unbiased=False) + 1e-6).rsqrt().float()
+    sc = torch.rand((rows + 12) // 13, device=DEV, generator=g) + 0.5
+    monkeypatch.setenv("FEDVIT_LN_REREAD", "1")
+    out = {}
+    for mode, grid in (("0", None), ("9", None), ("9", "3")):
+        monkeypatch.setenv("FEDVIT_LN_MINB", mode)
+        if grid:
+            monkeypatch.setenv("FEDVIT_LN_GRID", grid)
+        dg, db = torch.zeros(cols, device=DEV), torch.zeros(cols, device=DEV)
+        dx, dxlp = ops.layernorm_bwd(dy, x, gam, mean, rstd, dres, dg, db, True, sc, 13)
+        assert rel_err(dx, xr.grad + dres.double()) < 1e-5
+        assert rel_err(dxlp, dx * sc[torch.arange(rows, device=DEV) // 13, None]) < 4e-3
+        assert rel_err(dg, gr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
+        dx2, dxlp2 = ops.layernorm_bwd(dy, x, gam, mean, rstd, dres, dg, db, True)  # accumulates, no factor
+        assert torch.equal(dx2, dx) and rel_err(dxlp2, dx.bfloat16()) == 0.0
+        assert rel_err(dg, 2 * gr.grad) < 1e-5
+        out[(mode, grid)] = (dx, dxlp)
+    monkeypatch.delenv("FEDVIT_LN_GRID")
+    monkeypatch.delenv("FEDVIT_LN_MINB")
+    ops.layernorm_bwd(dy, x, gam, mean, rstd, dres, dg, db, True)  # back to the default for later tests
+    assert rel_err(out[("9", None)][0], out[("0", None)][0]) < 1e-6
+    assert torch.equal(out[("9", None)][0], out[("9", "3")][0])  # row arithmetic does not depend on the grid
+
+
 @pytest.mark.parametrize("B,N,H", [(2, 197, 3), (3, 64, 1), (2, 65, 2), (1, 1, 1), (2, 256, 2),   # one-tile tcgen05 kernels
                                    (1, 577, 2), (3, 257, 2), (5, 400, 3), (2, 768, 1),           # long-sequence tcgen05 kernels
                                    (1, 800, 1)])                                                 # mma.sync flash kernels
