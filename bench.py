@@ -321,7 +321,7 @@ def run_gpu_arm(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * IMG * IMG * 4 + BATCH * 8,
                     "d2h_bytes_per_step": 4,
                     "api": "fedvit_b200.train.train_one_epoch: pinned host batches copied per step on a side stream, "
-                           "every step's loss read back to the host (one step late, pinned scalar)"},
+                           "every step's loss read back to the host (two steps late, pinned scalars)"},
             "gpu_launches": launches,
             "roofline": {
                 "bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM: CTA-pair and single-CTA variants, all epilogues)",

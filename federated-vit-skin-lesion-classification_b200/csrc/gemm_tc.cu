@@ -60,7 +60,8 @@ struct GemmTcParams {
   int direct;  // epilogue without smem staging (needs 32-byte aligned rows of c / aux)
   // FEDVIT_GEMM_DBG (measurement / test switches): 1 = epilogue without global stores, 2 = no epilogue work,
   // 4 = direct (unstaged) epilogue, 8 = bias-gradient protocol without the reads, 16 = LSU flush instead of
-  // TMA stores, 32 = never use the CTA-pair kernel, 64 = use it for every legal shape (small test problems)
+  // TMA stores, 32 = never use the CTA-pair kernel, 64 = use it for every legal shape (small test problems),
+  // 256 = weight gradients stay on the single-CTA kernel
   int dbg;
 };
 
@@ -868,11 +869,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES2;
   uint64_t* tmem_full = empty_bar + STAGES2;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* a_full = tmem_empty + 2;      // bias-gradient mode, per CTA: this CTA's A tile of the stage has landed
+  uint64_t* a_ready = a_full + STAGES2;   // bias-gradient mode, leader only: both A tiles landed and summed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + STAGES2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  // weight-gradient mode with the fused bias gradient (column sums of the A operand, see below)
+  const bool colsum_mode = (EPI == FV_EPI_ACCUM) && p.colsum != nullptr;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
@@ -886,6 +891,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int s = 0; s < STAGES2; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_ready[s], 2);  // one agent warp of each CTA
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -902,24 +909,46 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   pdl_wait();
 
   const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
-  const int total_tiles = num_m2 * p.num_n_blocks;
+  const int tiles_mn = num_m2 * p.num_n_blocks;
+  const int total_tiles = tiles_mn * p.split_k;  // split-K (weight gradient): item = (k slice, m2, n_blk)
 
   if (warp == 0) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int m2 = tile / p.num_n_blocks;
-      const int n_blk = tile - m2 * p.num_n_blocks;
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m2 = mn / p.num_n_blocks;
+      const int n_blk = mn - m2 * p.num_n_blocks;
       const int row_a = m2 * 2 * BM + static_cast<int>(rank) * BM;
       const int row_b = n_blk * BN + static_cast<int>(rank) * HALF_BN;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * STAGE2_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
         if (elect_one()) {
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
-          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, row_a);  // A is K-major on this path
+          // bias-gradient mode: the A tile reports to THIS CTA's a_full (its agent warp sums it, then
+          // tells the leader); everything else reports straight to the leader's full barrier
+          uint64_t* bar_a = colsum_mode ? &a_full[stage] : &full_bar[stage];
+          if (colsum_mode) {
+            mbar_expect_tx(&a_full[stage], A_STAGE_BYTES);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * B2_STAGE_BYTES);
+          } else if (rank == 0) {
+            mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+          }
+          if (p.a_major == FV_MAJOR_K) {
+            if (colsum_mode) tma_load_2d(sa, &tmap_a, bar_a, kb * BK, row_a);
+            else tma_load_2d_pair(sa, &tmap_a, bar_a, kb * BK, row_a);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) {
+              if (colsum_mode) tma_load_2d(sa + j * (64 * BK * 2), &tmap_a, bar_a, row_a + j * 64, kb * BK);
+              else tma_load_2d_pair(sa + j * (64 * BK * 2), &tmap_a, bar_a, row_a + j * 64, kb * BK);
+            }
+          }
           if (p.b_major == FV_MAJOR_K) {
             tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BK, row_b);
           } else {
@@ -939,27 +968,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // instruction. (Issued from inside an `if (lane == 0)` region the compiler wraps every MMA in a
     // vote / broadcast loop — ~25 dependent instructions per MMA, as long as the MMA itself runs.)
     if (rank == 0) {
-      const uint32_t idesc = make_idesc(kFmtBF16, FV_MAJOR_K, p.b_major, 2 * BM, BN);
+      const uint32_t idesc = make_idesc(kFmtBF16, p.a_major, p.b_major, 2 * BM, BN);
+      const uint32_t a_lbo = p.a_major == FV_MAJOR_K ? 16 : 64 * BK * 2;
       const uint32_t b_lbo = p.b_major == FV_MAJOR_K ? 16 : 64 * BK * 2;
+      const uint32_t a_kstep = (p.a_major == FV_MAJOR_K ? 32 : 2048) >> 4;
       const uint32_t b_kstep = (p.b_major == FV_MAJOR_K ? 32 : 2048) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (colsum_mode) mbar_wait(&a_ready[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
-          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t da = make_smem_desc_sw128(sa, a_lbo, 1024);
           const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES, b_lbo, 1024);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_pair(tmem_d, da + k * 2, db + k * b_kstep, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_pair(tmem_d, da + k * a_kstep, db + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs
           }
           __syncwarp();
@@ -970,6 +1005,75 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if ((warp == 2 || warp == 3) && colsum_mode) {
+    // ------------------------------- bias-gradient agents (both CTAs) ------------------------
+    // Same job as in the single-CTA kernel (column sums of the dY tiles while they sit in shared
+    // memory), different hand-shake: here an A tile reports to the a_full barrier of the CTA it
+    // lands in; the stage's agent warp (warp 2: even stages, warp 3: odd) sums its share and then
+    // arrives on the LEADER's a_ready barrier, which the MMA thread waits for next to the B bytes.
+    // The agents run ahead of the MMA by up to the ring depth, so the sums are normally finished
+    // long before the tensor core reaches the stage, and the slot is released by the MMA commit
+    // alone (no second arrival on the empty barrier, no agent on the ring's critical path).
+    float* red = reinterpret_cast<float*>(tmem_slot + 8);  // 128 floats after the barriers
+    const int agent = warp - 2;
+    const int t64 = threadIdx.x - 64;
+    int iter = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m2 = mn / p.num_n_blocks;
+      const int n_blk = mn - m2 * p.num_n_blocks;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+      float cs[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cs[i] = 0.f;
+      for (int kb = kb0; kb < kb1; ++kb, ++iter) {
+        const int st = iter % STAGES2;
+        if ((st & 1) != agent) continue;
+        mbar_wait(&a_full[st], (iter / STAGES2) & 1);
+        // the pairs that work on the same row block (one per n_blk) split its k-slices round-robin
+        if (kb % p.num_n_blocks == n_blk && !(p.dbg & 8)) {
+          const uint8_t* sa = smem + st * STAGE2_BYTES;
+#pragma unroll 4
+          for (int g = 0; g < 16; ++g) {
+            const int k = g * 4 + (lane >> 3);
+            const int off = k * 128 + (((lane & 7) ^ (k & 7)) << 4);
+#pragma unroll
+            for (int bx = 0; bx < 2; ++bx) {
+              const uint4 w = *reinterpret_cast<const uint4*>(sa + bx * (64 * BK * 2) + off);
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                cs[bx * 8 + 2 * j] += __uint_as_float(ww[j] << 16);
+                cs[bx * 8 + 2 * j + 1] += __uint_as_float(ww[j] & 0xFFFF0000u);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&a_ready[st]);
+      }
+      red[t64] = 0.f;
+      red[t64 + 64] = 0.f;
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {  // token rows (lane >> 3) -> lanes 0..7
+        cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+        cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(&red[(i >> 3) * 64 + lane * 8 + (i & 7)], cs[i]);
+      }
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const long long gcol = static_cast<long long>(m2) * 2 * BM + rank * BM + t64 + j * 64;
+        if (gcol < p.M) atomicAdd(p.colsum + gcol, red[t64 + j * 64]);
+      }
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+    }
   } else if (warp >= 4) {
     // ------------------------------- epilogue (both CTAs, own 128 rows) ----------------------
     const int wq = warp & 3;
@@ -978,8 +1082,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t acc_phase = 0;
     bool pending = false;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int m2 = tile / p.num_n_blocks;
-      const int n_blk = tile - m2 * p.num_n_blocks;
+      const int mn = tile % tiles_mn;
+      const int m2 = mn / p.num_n_blocks;
+      const int n_blk = mn - m2 * p.num_n_blocks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const long long row0 = static_cast<long long>(m2) * 2 * BM + rank * BM + wq * 32;
@@ -1095,7 +1200,7 @@ static int launch_gemm_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const C
                                        GEMM_SMEM_BYTES));
     configured = true;
   }
-  const int total = static_cast<int>(ceil_div(p.M, 2 * BM)) * p.num_n_blocks;
+  const int total = static_cast<int>(ceil_div(p.M, 2 * BM)) * p.num_n_blocks * p.split_k;
   int clusters = num_sms() / 2;
   if (clusters > total) clusters = total;
   FV_CHECK_CUDA(fv::launch_pdl_cluster(gemm_tc2_kernel<EPI, BF16>, dim3(2 * clusters), dim3(GEMM_THREADS),
@@ -1205,10 +1310,16 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // CTA-pair kernel (256 x 256 tiles): forward / dgrad shapes with enough tiles to fill the pairs
-  const bool pair = a_major == FV_MAJOR_K && split_k == 1 && p.tma_out && !(p.dbg & 32) &&
-                    (epilogue == FV_EPI_NONE || epilogue == FV_EPI_RESIDUAL || epilogue == FV_EPI_GELU ||
-                     epilogue == FV_EPI_DGELU) &&
-                    (ceil_div(m, 2 * BM) * p.num_n_blocks >= num_sms() / 2 || (p.dbg & 64));
+  const int64_t pair_items = ceil_div(m, 2 * BM) * p.num_n_blocks * p.split_k;
+  const bool pair_fwd = a_major == FV_MAJOR_K && p.split_k == 1 &&
+                        (epilogue == FV_EPI_NONE || epilogue == FV_EPI_RESIDUAL || epilogue == FV_EPI_GELU ||
+                         epilogue == FV_EPI_DGELU) &&
+                        (pair_items >= num_sms() / 2 || (p.dbg & 64));
+  // weight gradient (MN-major x MN-major, split-K accumulate) on the pair kernel as well: a third
+  // less operand traffic per flop than the 128 x 256 single-CTA tile; FEDVIT_GEMM_DBG & 256 = never
+  const bool pair_wgrad = epilogue == FV_EPI_ACCUM && a_major == FV_MAJOR_MN && b_major == FV_MAJOR_MN &&
+                          !(p.dbg & 256) && (pair_items >= num_sms() / 4 || (p.dbg & 64));
+  const bool pair = p.tma_out && !(p.dbg & 32) && (pair_fwd || pair_wgrad);
   if (pair) {
     // B map box: this CTA's 128-row half (K-major) — the MN-major map already uses 64-column boxes
     if (b_major == FV_MAJOR_K) {
@@ -1226,6 +1337,7 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
       case FV_EPI_DGELU:
         return p.c_bf16 ? launch_gemm_tc2<FV_EPI_DGELU, true>(ta, tb, tc, tx, p, st)
                         : launch_gemm_tc2<FV_EPI_DGELU, false>(ta, tb, tc, tx, p, st);
+      case FV_EPI_ACCUM: return launch_gemm_tc2<FV_EPI_ACCUM, false>(ta, tb, tc, tx, p, st);
     }
   }
   switch (epilogue) {

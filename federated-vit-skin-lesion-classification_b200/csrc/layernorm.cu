@@ -471,10 +471,15 @@ layernorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const float* __r
       if (lp_scale != nullptr) lps_n = __ldg(lp_scale + (row + stride) / rows_per_scale);
     }
     mbar_wait(&full_bar[slot], phase);
-    float4 xh[NVW], rr[NVW];
-    uint2 dd[NVW];
-    if (live) {
-      const uint8_t* base = ring + slot * GROUP_BYTES + warp * ROW_BYTES;
+    // Rows up to 768 columns are pulled into registers whole and the slot is handed back at once;
+    // wider rows would spill (168 registers per thread), so their residual gradient stays in the
+    // ring until the output pass and the slot is released after it.
+    constexpr bool LATE = NVW >= 7;
+    float4 xh[NVW], rr[LATE ? 1 : NVW];
+    uint2 dd[LATE ? 1 : NVW];
+    const uint8_t* base = ring + slot * GROUP_BYTES + warp * ROW_BYTES;
+    uint64_t* my_empty = &empty_bar[slot];
+    if (live && !LATE) {
 #pragma unroll
       for (int i = 0; i < NVW; ++i) {
         xh[i] = *reinterpret_cast<const float4*>(base + (i * 32 + lane) * 16);
@@ -482,17 +487,21 @@ layernorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const float* __r
         dd[i] = *reinterpret_cast<const uint2*>(base + 2 * X_BYTES + (i * 32 + lane) * 8);
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[slot]);  // the row is in registers: the slot can be refilled
+    if (!LATE || !live) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(my_empty);  // the row is in registers: the slot can be refilled
+    }
     if (++slot == depth) { slot = 0; phase ^= 1; }
     if (!live) continue;
     float4 gy[NVW];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NVW; ++i) {
-      const float2 lo = unpack_bf16(dd[i].x), hi = unpack_bf16(dd[i].y);
+      const uint2 dw = LATE ? *reinterpret_cast<const uint2*>(base + 2 * X_BYTES + (i * 32 + lane) * 8)
+                            : dd[LATE ? 0 : i];
+      const float2 lo = unpack_bf16(dw.x), hi = unpack_bf16(dw.y);
       const float4 d = make_float4(lo.x, lo.y, hi.x, hi.y);
-      const float4 xv = xh[i];
+      const float4 xv = LATE ? *reinterpret_cast<const float4*>(base + (i * 32 + lane) * 16) : xh[i];
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       const float4 g = GM_REGS ? gm[GM_REGS ? i : 0] : __ldg(g4 + i * 32 + lane);
       gy[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
@@ -508,11 +517,13 @@ layernorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const float* __r
     uint2* lrow = reinterpret_cast<uint2*>(dx_lp + row * COLS);
 #pragma unroll
     for (int i = 0; i < NVW; ++i) {
+      const float4 r = LATE ? *reinterpret_cast<const float4*>(base + X_BYTES + (i * 32 + lane) * 16)
+                            : rr[LATE ? 0 : i];
       float4 o;
-      o.x = rs * (gy[i].x - s1 - xh[i].x * s2) + rr[i].x;
-      o.y = rs * (gy[i].y - s1 - xh[i].y * s2) + rr[i].y;
-      o.z = rs * (gy[i].z - s1 - xh[i].z * s2) + rr[i].z;
-      o.w = rs * (gy[i].w - s1 - xh[i].w * s2) + rr[i].w;
+      o.x = rs * (gy[i].x - s1 - xh[i].x * s2) + r.x;
+      o.y = rs * (gy[i].y - s1 - xh[i].y * s2) + r.y;
+      o.z = rs * (gy[i].z - s1 - xh[i].z * s2) + r.z;
+      o.w = rs * (gy[i].w - s1 - xh[i].w * s2) + r.w;
       orow[i * 32 + lane] = o;
       if (dx_lp != nullptr) {
         uint2 pk;
@@ -520,6 +531,10 @@ layernorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const float* __r
         pk.y = pack_bf16(o.z * lps, o.w * lps);
         lrow[i * 32 + lane] = pk;
       }
+    }
+    if (LATE) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(my_empty);
     }
   }
   // dgamma / dbeta: the eight warps' register partials meet in the (now idle) ring

@@ -25,6 +25,7 @@ accumulator; one NCCL allreduce; scheduler stepped once per round.
 from __future__ import annotations
 
 import argparse
+import collections
 import logging
 import os
 import sys
@@ -149,12 +150,14 @@ def train_one_epoch(model: nn.Module, loader, criterion, optimizer, scheduler, s
     n_steps = len(loader)
     optimizer.zero_grad(set_to_none=True)
     # training.sync_loss_every_step: read every step's loss back to the host like the reference does
-    # (train.py:164) — but one step late, from a pinned buffer, so the device->host read of step i
-    # overlaps the kernels of step i+1 instead of draining the GPU every iteration.
+    # (train.py:164) — but `training.loss_read_lag` steps late (default 2), from pinned scalars, so
+    # the device->host read of step i overlaps the kernels of the following steps instead of draining
+    # the GPU every iteration, and a host hiccup of up to one step time never starves the device.
     sync_every_step = bool(t.get("sync_loss_every_step", False))
+    lag = max(1, int(t.get("loss_read_lag", 2)))
     host_loss = 0.0
-    pending = None  # (event, pinned scalar, weight) of the previous step
-    pinned = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(2)] if sync_every_step else None
+    pending = collections.deque()  # (event, pinned scalar, weight) of the last `lag` steps
+    pinned = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(lag + 1)] if sync_every_step else None
     for step, batch in enumerate(_device_batches(loader, device)):
         images, labels, meta = batch["image"], batch["label"], batch.get("metadata")
         bs = images.size(0)
@@ -187,21 +190,22 @@ def train_one_epoch(model: nn.Module, loader, criterion, optimizer, scheduler, s
                 ema.update()
 
         if sync_every_step:
-            buf = pinned[step & 1]
+            buf = pinned[step % (lag + 1)]
             buf.copy_(loss.detach(), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-            if pending is not None:
-                pending[0].synchronize()
-                host_loss += float(pending[1]) * pending[2]
-            pending = (ev, buf, accum * bs)
+            pending.append((ev, buf, accum * bs))
+            if len(pending) > lag:
+                old_ev, old_buf, w = pending.popleft()
+                old_ev.synchronize()
+                host_loss += float(old_buf) * w
         else:
             loss_sum += loss.detach() * (accum * bs)
         seen += bs
     if sync_every_step:
-        if pending is not None:
-            pending[0].synchronize()
-            host_loss += float(pending[1]) * pending[2]
+        for old_ev, old_buf, w in pending:
+            old_ev.synchronize()
+            host_loss += float(old_buf) * w
         return host_loss / max(seen, 1)
     return float(loss_sum.item()) / max(seen, 1)
 

@@ -123,16 +123,18 @@ def _grad_buffer(p: nn.Parameter) -> Tensor:
 
 def _split_k_for(out_rows: int, out_cols: int, k: int, sms: int = 148) -> int:
     """K slices for a weight-gradient GEMM (small M x N, huge K = tokens): the smallest split whose
-    tile count fills whole waves of the persistent grid best (qkv at ViT-B: 54 tiles -> 8 slices =
-    2.92 waves, not 2 slices = 0.73 of one wave), with at least 16 k-blocks per slice."""
-    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
+    item count fills whole waves of the persistent grid best, with at least 16 k-blocks per slice.
+    The weight gradient runs on the CTA-pair kernel: 256 x 256 tiles on sms // 2 pairs (fc1 at
+    ViT-B: 36 tiles -> 2 slices = 72 items on 74 pairs; qkv: 27 tiles -> 8 slices = 2.92 waves)."""
+    tiles = ((out_rows + 255) // 256) * ((out_cols + 255) // 256)
+    units = max(1, sms // 2)
     kb = (k + 63) // 64
     best, best_eff = 1, 0.0
     for s in range(1, 17):
         if s > 1 and kb // s < 16:
             break
         t = tiles * s
-        eff = t / (((t + sms - 1) // sms) * sms)
+        eff = t / (((t + units - 1) // units) * units)
         if eff > best_eff + 0.01:
             best, best_eff = s, eff
     return best

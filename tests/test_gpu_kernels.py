@@ -351,7 +351,10 @@ def test_elementwise_helpers():
     assert launch_count() == n0 + 1
 
 
-@pytest.mark.parametrize("tokens,out_f,in_f,sk", [(1000, 776, 328, 3), (50432, 768, 768, 8), (197 * 4, 192, 768, 1), (37, 8, 16, 1)])
+@pytest.mark.parametrize("tokens,out_f,in_f,sk", [(1000, 776, 328, 3), (50432, 768, 768, 8), (197 * 4, 192, 768, 1), (37, 8, 16, 1),
+                                                  # CTA-pair weight-gradient kernel (>= 37 items): ragged M / N / K tails,
+                                                  # several items per pair, one n-block (every k-slice summed by one pair)
+                                                  (1031, 1000, 520, 4), (4099, 2304, 768, 8), (2050, 3072, 200, 4)])
 def test_wgrad_with_fused_bias_gradient(tokens, out_f, in_f, sk):
     g = _gen(tokens + out_f)
     dy = torch.randn(tokens, out_f, device=DEV, generator=g).bfloat16()

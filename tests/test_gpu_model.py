@@ -210,6 +210,23 @@ def test_train_one_epoch_matches_oracle_local_epoch(golden_rgb):
     assert rel_err(m2.classifier[0].weight, ora2.classifier[0].weight) < POST_ADAM_TOL
 
 
+@pytest.mark.parametrize("lag", [1, 2, 5])
+def test_per_step_loss_readback_matches_device_accumulation(golden_rgb, lag):
+    """training.sync_loss_every_step (the reference reads loss.item() every step, train.py:164): the
+    lagged pinned read-back returns the same epoch loss as the device-side accumulation, whatever the
+    lag (also larger than the number of steps)."""
+    loader = data.SyntheticClientLoader(0, 24, 6, 32, channels=3, num_classes=7, pin=False)
+    got = []
+    for sync in (False, True):
+        cfg = micro_config()
+        cfg["training"]["sync_loss_every_step"] = sync
+        cfg["training"]["loss_read_lag"] = lag
+        m = _fixture_model(golden_rgb)
+        opt = optim.FusedAdamW(model.get_layerwise_lr_groups(m, 1e-3, 0.75, 1e-2), weight_decay=1e-2, arena=FlatArena(m))
+        got.append(train.train_one_epoch(m, loader, losses.build_loss(cfg), opt, None, None, None, DEV, cfg, 1, None))
+    assert got[1] == pytest.approx(got[0], rel=1e-6)
+
+
 def test_validate_reports_reference_metrics(golden_rgb):
     cfg = micro_config()
     m = _fixture_model(golden_rgb)
