@@ -82,6 +82,20 @@ def main() -> None:
         print(f"  host enqueue time {cpu_ms:6.2f} ms/step (GPU step time below: the host has to stay under it)")
         return t0.elapsed_time(t1) / steps
 
+    # pinned host -> device bandwidth of one batch (the per-step copy of the end-to-end path)
+    dst = torch.empty_like(dev_x[:B])
+    for _ in range(2):
+        dst.copy_(host_x[:B], non_blocking=True)
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for i in range(8):
+        dst.copy_(host_x[(i % pool) * B:(i % pool + 1) * B], non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    ms = h0.elapsed_time(h1) / 8
+    print(f"pinned H2D of one batch ({dst.numel() * 4 / 1e6:.0f} MB): {ms:.2f} ms = {dst.numel() * 4 / ms / 1e6:.1f} GB/s")
+
     for rep in range(2):
         print(f"plain step loop (device batches)           {plain():7.2f} ms/step")
         print(f"train_one_epoch, device batches, no sync   {run(True, False):7.2f}")
