@@ -90,7 +90,7 @@ gemm_simt_kernel(const SimtParams p) {
         if (p.row_scale != nullptr) v *= p.row_scale[row / p.rows_per_scale];
         C[row * p.ldc + col] = v + p.aux[row * p.ldaux + col];
       } else if (EPI == FV_EPI_GELU) {
-        p.aux[row * p.ldaux + col] = gelu_erf_grad(v);  // kept for the backward instead of v itself
+        if (p.aux != nullptr) p.aux[row * p.ldaux + col] = gelu_erf_grad(v);  // kept for the backward instead of v itself
         C[row * p.ldc + col] = gelu_erf(v);
       } else if (EPI == FV_EPI_DGELU) {
         C[row * p.ldc + col] = v * p.aux[row * p.ldaux + col];
@@ -124,8 +124,7 @@ extern "C" int fv_gemm_f32(const float* a, int64_t a_row_stride, int64_t a_col_s
   FV_CHECK_ARG(m < (1LL << 31) && n < (1LL << 31) && k < (1LL << 31) && batch <= 65535,
                "fv_gemm_f32: size out of range (batch <= 65535)");
   FV_CHECK_ARG(epilogue >= FV_EPI_NONE && epilogue <= FV_EPI_PATCH, "fv_gemm_f32: bad epilogue");
-  if (epilogue == FV_EPI_RESIDUAL || epilogue == FV_EPI_GELU || epilogue == FV_EPI_DGELU ||
-      epilogue == FV_EPI_PATCH)
+  if (epilogue == FV_EPI_RESIDUAL || epilogue == FV_EPI_DGELU || epilogue == FV_EPI_PATCH)
     FV_CHECK_ARG(aux != nullptr, "fv_gemm_f32: epilogue needs aux");
   if (epilogue == FV_EPI_PATCH) FV_CHECK_ARG(tokens_per_img > 0, "fv_gemm_f32: tokens_per_img");
   FV_CHECK_ARG(ceil_div(m, SM_BM) <= 65535, "fv_gemm_f32: m too large for the grid");

@@ -428,8 +428,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
             }
             f32x2 cdf, pdf;
             gelu_parts2(u0, u1, u, cdf, pdf);
-            v[i] = f2_fma(u, pdf, cdf);
             const f32x2 act = f2_mul(u, cdf);
+            if (p.aux == nullptr) {  // forward-only: no derivative, the activation takes the staging tile directly
+              v[i] = act;
+              continue;
+            }
+            v[i] = f2_fma(u, pdf, cdf);
             if (bf16) {
               gbuf[c * 16 + i] = pack_bf16(act);
             } else {
@@ -442,7 +446,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
       }
     }
     __syncwarp();
-    if (EPI == FV_EPI_GELU) {
+    if (EPI == FV_EPI_GELU && p.aux != nullptr) {
       stage_store<EPI>(p, map_aux, stg, p.aux, p.ldaux, go, lane, pending);  // gelu'(u) -> aux
       __syncwarp();
       stage_acquire(lane, pending);
@@ -1246,8 +1250,8 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
   FV_CHECK_ARG(epilogue >= FV_EPI_NONE && epilogue <= FV_EPI_PATCH, "fv_gemm_bf16: bad epilogue");
   if (epilogue == FV_EPI_RESIDUAL || epilogue == FV_EPI_ACCUM || epilogue == FV_EPI_PATCH)
     FV_CHECK_ARG(c_dtype == FV_F32, "fv_gemm_bf16: this epilogue writes fp32");
-  if (epilogue == FV_EPI_RESIDUAL || epilogue == FV_EPI_GELU || epilogue == FV_EPI_DGELU ||
-      epilogue == FV_EPI_PATCH)
+  if (epilogue == FV_EPI_RESIDUAL || epilogue == FV_EPI_DGELU || epilogue == FV_EPI_PATCH ||
+      (epilogue == FV_EPI_GELU && aux != nullptr))  // GELU: aux NULL == activation only (forward-only use)
     FV_CHECK_ARG(aux != nullptr && ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
                  "fv_gemm_bf16: epilogue needs a 16-byte aligned aux with ldaux %% 8 == 0");
   if (epilogue == FV_EPI_PATCH) FV_CHECK_ARG(tokens_per_img > 0, "fv_gemm_bf16: tokens_per_img");
@@ -1285,7 +1289,7 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
     const int64_t ae = (epilogue == FV_EPI_RESIDUAL) ? 4 : ce;
     bool ok = (reinterpret_cast<uintptr_t>(c) & 31) == 0 && (ldc * ce) % 32 == 0;
     if (aux != nullptr) ok = ok && (reinterpret_cast<uintptr_t>(aux) & 31) == 0 && (ldaux * ae) % 32 == 0;
-    p.direct = (ok && (p.dbg & 4)) ? 1 : 0;
+    p.direct = (ok && (p.dbg & 4) && !(epilogue == FV_EPI_GELU && aux == nullptr)) ? 1 : 0;
   }
   p.gw = p.gh = p.chans = p.ph_per_tile = p.tiles_per_img = 0;
   FV_CHECK_ARG(p.colsum == nullptr || (epilogue == FV_EPI_ACCUM && a_major == FV_MAJOR_MN),
@@ -1302,7 +1306,7 @@ extern "C" int fv_gemm_bf16(const void* a, int a_major, int64_t lda, const void*
   if (p.tma_out) {
     rc = make_out_map(&tc, c, p.c_bf16 != 0, m, n, ldc);
     if (rc != FV_OK) return rc;
-    if (epilogue == FV_EPI_GELU) {
+    if (epilogue == FV_EPI_GELU && aux != nullptr) {
       rc = make_out_map(&tx, aux, p.c_bf16 != 0, m, n, ldaux);
       if (rc != FV_OK) return rc;
     }

@@ -136,6 +136,13 @@ def gemm_gelu(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor, pre: Te
     _gemm_impl(a, b, bias, out, pre, MAJOR_K, MAJOR_K, EPI["gelu"], 1, 0)
 
 
+@torch.library.custom_op("fedvit::gemm_gelu_fwd", mutates_args=("out",))
+def gemm_gelu_fwd(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor) -> None:
+    """out = gelu_erf(a @ b^T + bias) without the derivative output — the forward-only (eval /
+    no-grad) form of :func:`gemm_gelu`: half the epilogue's stores."""
+    _gemm_impl(a, b, bias, out, None, MAJOR_K, MAJOR_K, EPI["gelu"], 1, 0)
+
+
 @torch.library.custom_op("fedvit::linear_residual", mutates_args=("out",))
 def linear_residual(a: Tensor, w: Tensor, bias: Optional[Tensor], residual: Tensor, row_scale: Optional[Tensor],
                     rows_per_scale: int, out: Tensor) -> None:

@@ -329,9 +329,13 @@ class VisionTransformer(nn.Module):
             ops.linear_residual(o, self._w(at.proj.weight, lp), at.proj.bias.detach(), x, s1, N, x1)
             h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2.weight.detach(), n2.bias.detach(), n2.eps, lp)
             hid = mlp.fc1.weight.shape[0]
-            u = torch.empty((M, hid), device=dev, dtype=act)
             a = torch.empty((M, hid), device=dev, dtype=act)
-            ops.gemm_gelu(h2, self._w(mlp.fc1.weight, lp), mlp.fc1.bias.detach(), a, u)
+            if save:
+                u = torch.empty((M, hid), device=dev, dtype=act)  # gelu'(fc1 output), all the backward needs
+                ops.gemm_gelu(h2, self._w(mlp.fc1.weight, lp), mlp.fc1.bias.detach(), a, u)
+            else:  # forward only: no derivative output
+                u = None
+                ops.gemm_gelu_fwd(h2, self._w(mlp.fc1.weight, lp), mlp.fc1.bias.detach(), a)
             x2 = torch.empty((M, D), device=dev, dtype=torch.float32)
             ops.linear_residual(a, self._w(mlp.fc2.weight, lp), mlp.fc2.bias.detach(), x1, s2, N, x2)
             if save:

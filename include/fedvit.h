@@ -67,7 +67,8 @@ int64_t fv_launch_count(void);
  *   bias            : fp32 [N] or NULL
  *   c, c_dtype, ldc : output (FV_F32 or FV_BF16)
  *   aux             : FV_EPI_RESIDUAL -> fp32 residual [M,ldaux]; FV_EPI_GELU -> second output, the
- *                     GELU derivative at the pre-activation (c_dtype); FV_EPI_DGELU -> that tensor;
+ *                     GELU derivative at the pre-activation (c_dtype), or NULL when only the activation
+ *                     is wanted (forward-only / eval); FV_EPI_DGELU -> that tensor;
  *                     FV_EPI_PATCH -> fp32 pos_embed [(tokens_per_img+1), N]
  *   split_k         : >1 only with FV_EPI_ACCUM: K is cut in split_k slices, each atomically
  *                     accumulated into fp32 C.

@@ -82,6 +82,13 @@ def test_gemm_bf16_epilogues(m, n, k):
         ops.gemm_gelu(a, b, bias, o, dact)
         assert rel_err(o, act_ref) < tol
         assert rel_err(dact, pre.grad) < tol
+        o2 = torch.full((m, n), 7.0, device=DEV, dtype=dt)
+        ops.gemm_gelu_fwd(a, b, bias, o2)  # forward-only form (no derivative output): the same activation bits
+        assert torch.equal(o2, o)
+    o32, o32b = torch.empty(m, n, device=DEV), torch.empty(m, n, device=DEV)
+    ops.gemm_gelu(a.float(), b.float(), bias, o32, torch.empty(m, n, device=DEV))  # fp32 FFMA path
+    ops.gemm_gelu_fwd(a.float(), b.float(), bias, o32b)
+    assert torch.equal(o32, o32b) and rel_err(o32, act_ref) < 1e-5
     # dgrad fused with the saved GELU derivative
     g1 = torch.randn(m, n, device=DEV, generator=g)
     out = torch.empty(m, n, device=DEV)
