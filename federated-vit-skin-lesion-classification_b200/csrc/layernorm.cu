@@ -1,4 +1,8 @@
-// layernorm.cu — fused LayerNorm forward / backward (HBM-bound; one warp per row).
+// layernorm.cu — fused LayerNorm forward / backward (HBM-bound).
+//   forward            one warp per row, registers only
+//   backward, default  bulk-copy ring: cp.async.bulk streams whole rows into shared memory, one
+//                      consumer warp per row (bf16 dy + residual gradient, cols % 128 == 0)
+//   backward, other    register-pipelined, two warps per row (fp32 dy, no residual gradient, odd widths)
 //
 // Replaces F.layer_norm behind timm's Block.norm1 / norm2 and VisionTransformer.norm (reference
 // call site model.py:193) and its autograd backward (train.py:153). Statistics are fp32 whatever

@@ -8,6 +8,9 @@ Measures, at the ViT-B/16 batch-256 shapes (50432 rows x 768):
   4. GEMM on G SMs and LayerNorm backward on the other 148 - G, launched on two streams.
 
     python tools/overlap_probe.py > gpurun_out/overlap_probe.txt
+
+Parts 3 and 4 cap the grid of the single-CTA GEMM kernel (FEDVIT_GEMM_GRID): run them with
+FEDVIT_GEMM_DBG=256, which keeps the weight gradients off the CTA-pair kernel they use by default now.
 """
 from __future__ import annotations
 
