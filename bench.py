@@ -202,6 +202,7 @@ def run_gpu_arm(args) -> None:
         saved_stdout = None
 
     cfg = model_config()
+    cfg["model"]["cls_only_last_block"] = bool(args.cls_only_last_block)
     utils.seed_everything(42)
     net = model.build_model(cfg).to(dev).train()
     arena = FlatArena(net)
@@ -316,7 +317,11 @@ def run_gpu_arm(args) -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.gpus),
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": dict(workload_config(args.gpus),
+                           **({"cls_only_last_block": "opt-in: last block's proj / LN2 / MLP on the cls rows only "
+                                                      "(exact; FLOP-based fractions below still count the dense model)"}
+                              if args.cls_only_last_block else {})),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * IMG * IMG * 4 + BATCH * 8,
                     "d2h_bytes_per_step": 4,
@@ -365,6 +370,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="fedvit", choices=["fedvit", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cls-only-last-block", action="store_true",
+                    help="opt-in model.cls_only_last_block: the last block's token-wise tail on the cls rows only "
+                         "(same logits / gradients, ~4 %% fewer FLOPs); NOT the default measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "fedvit":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

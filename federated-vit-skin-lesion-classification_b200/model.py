@@ -180,7 +180,7 @@ def build_model(config: dict) -> ISICClassifier:
     meta = m.get("metadata", {})
     head = m.get("classifier", {})
     masked = config.get("data", {}).get("use_segmentation_mask", False)
-    return ISICClassifier(
+    net = ISICClassifier(
         backbone_name=m.get("backbone", _DEFAULT_BACKBONE),
         num_classes=m.get("num_classes", 8),
         image_size=m.get("image_size", 384),
@@ -195,3 +195,7 @@ def build_model(config: dict) -> ISICClassifier:
         cls_hidden_dim=int(head.get("hidden_dim", 512)),
         cls_dropout=float(head.get("dropout", 0.5)),
     )
+    # additive key (not in the reference's config.yaml): run the last block's token-wise tail on the cls
+    # rows only — see VisionTransformer.cls_only_last_block; off unless asked for
+    net.backbone.cls_only_last_block = bool(m.get("cls_only_last_block", False))
+    return net

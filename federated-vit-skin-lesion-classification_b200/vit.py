@@ -163,7 +163,7 @@ def weight_operand(p: nn.Parameter, lp: bool) -> Tensor:
 
 
 class _Saved:
-    __slots__ = ("lp", "B", "N", "img", "patches", "blocks", "cls_rows", "meanf", "rstdf")
+    __slots__ = ("lp", "B", "N", "img", "patches", "blocks", "cls_rows", "meanf", "rstdf", "cls_only")
 
 
 class VisionTransformer(nn.Module):
@@ -186,6 +186,13 @@ class VisionTransformer(nn.Module):
         dpr = [r.item() for r in torch.linspace(0, drop_path_rate, depth)]
         self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio, dpr[i]) for i in range(depth)])
         self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        # Opt-in (``model.cls_only_last_block``): the head reads the cls token only, and everything after the
+        # last block's attention is token-wise, so the other 196 rows of that block's proj / LN2 / MLP
+        # (forward) and of their gradients (backward: exactly zero) never reach the loss. With the switch on
+        # those kernels run on the B cls rows instead of B*N — same logits, same parameter gradients
+        # (up to summation order), ~4 % fewer FLOPs per ViT-B/16 step. Off by default: the dense schedule is
+        # what timm executes.
+        self.cls_only_last_block = False
         self.init_weights()
 
     def init_weights(self) -> None:
@@ -317,7 +324,9 @@ class VisionTransformer(nn.Module):
             st.patches = patches
             st.img = img
             st.blocks = []
-        for blk in self.blocks:
+        nblk = len(self.blocks)
+        cls_only = False
+        for bi, blk in enumerate(self.blocks):
             n1, n2, at, mlp = blk.norm1, blk.norm2, blk.attn, blk.mlp
             h, mean1, rstd1 = ops.layernorm_fwd(x, n1.weight.detach(), n1.bias.detach(), n1.eps, lp)
             qkv = torch.empty((M, 3 * D), device=dev, dtype=act)
@@ -325,28 +334,36 @@ class VisionTransformer(nn.Module):
             o, aux = self._attention_fwd(qkv, B, N, lp)
             s1 = self._drop_path_scale(blk.drop_path_rate, B, dev)
             s2 = self._drop_path_scale(blk.drop_path_rate, B, dev)
-            x1 = torch.empty((M, D), device=dev, dtype=torch.float32)
-            ops.linear_residual(o, self._w(at.proj.weight, lp), at.proj.bias.detach(), x, s1, N, x1)
+            cls_only = self.cls_only_last_block and bi == nblk - 1
+            rows, per = (B, 1) if cls_only else (M, N)  # rows the token-wise tail runs on, rows per sample
+            if cls_only:
+                o_in = o.view(B, N, D)[:, 0].contiguous()
+                x_in = x.view(B, N, D)[:, 0].contiguous()
+            else:
+                o_in, x_in = o, x
+            x1 = torch.empty((rows, D), device=dev, dtype=torch.float32)
+            ops.linear_residual(o_in, self._w(at.proj.weight, lp), at.proj.bias.detach(), x_in, s1, per, x1)
             h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2.weight.detach(), n2.bias.detach(), n2.eps, lp)
             hid = mlp.fc1.weight.shape[0]
-            a = torch.empty((M, hid), device=dev, dtype=act)
+            a = torch.empty((rows, hid), device=dev, dtype=act)
             if save:
-                u = torch.empty((M, hid), device=dev, dtype=act)  # gelu'(fc1 output), all the backward needs
+                u = torch.empty((rows, hid), device=dev, dtype=act)  # gelu'(fc1 output), all the backward needs
                 ops.gemm_gelu(h2, self._w(mlp.fc1.weight, lp), mlp.fc1.bias.detach(), a, u)
             else:  # forward only: no derivative output
                 u = None
                 ops.gemm_gelu_fwd(h2, self._w(mlp.fc1.weight, lp), mlp.fc1.bias.detach(), a)
-            x2 = torch.empty((M, D), device=dev, dtype=torch.float32)
-            ops.linear_residual(a, self._w(mlp.fc2.weight, lp), mlp.fc2.bias.detach(), x1, s2, N, x2)
+            x2 = torch.empty((rows, D), device=dev, dtype=torch.float32)
+            ops.linear_residual(a, self._w(mlp.fc2.weight, lp), mlp.fc2.bias.detach(), x1, s2, per, x2)
             if save:
                 st.blocks.append((x, h, mean1, rstd1, qkv, o, aux, x1, h2, mean2, rstd2, u, a, s1, s2))
             x = x2
 
-        cls_rows = x.view(B, N, D)[:, 0].contiguous()
+        cls_rows = x if cls_only else x.view(B, N, D)[:, 0].contiguous()
         nf = self.norm
         feats, meanf, rstdf = ops.layernorm_fwd(cls_rows, nf.weight.detach(), nf.bias.detach(), nf.eps, False)
         if save:
             st.cls_rows, st.meanf, st.rstdf = cls_rows, meanf, rstdf
+            st.cls_only = cls_only
         return feats, st
 
     # ------------------------------------------------------------------------------------------
@@ -377,7 +394,8 @@ class VisionTransformer(nn.Module):
         return dx
 
     def _ln_bwd(self, dy: Tensor, x: Tensor, ln: nn.LayerNorm, mean: Tensor, rstd: Tensor,
-                dres: Optional[Tensor], lp: bool, branch_scale: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+                dres: Optional[Tensor], lp: bool, branch_scale: Optional[Tensor] = None,
+                rows_per_sample: Optional[int] = None) -> Tuple[Tensor, Tensor]:
         """Returns (dx fp32, the gradient the preceding sub-layer's branch GEMMs consume): dx in the
         GEMM operand type, times that branch's stochastic-depth factor when it has one."""
         if ln.weight.requires_grad:
@@ -385,13 +403,14 @@ class VisionTransformer(nn.Module):
         else:
             dg = torch.zeros_like(ln.weight)
             db = torch.zeros_like(ln.bias)
-        rows_per = self.num_tokens if branch_scale is not None else 0
+        rows_per_sample = self.num_tokens if rows_per_sample is None else rows_per_sample
+        rows_per = rows_per_sample if branch_scale is not None else 0
         dx, dx_lp = ops.layernorm_bwd(dy, x, ln.weight.detach(), mean, rstd, dres, dg, db, lp,
                                       branch_scale if lp else None, rows_per)
         if lp:
             return dx, dx_lp
         if branch_scale is not None:  # fp32 parity path: explicit scaled copy
-            return dx, (dx.view(-1, self.num_tokens, dx.shape[1]) * branch_scale.view(-1, 1, 1)).view_as(dx)
+            return dx, (dx.view(-1, rows_per_sample, dx.shape[1]) * branch_scale.view(-1, 1, 1)).view_as(dx)
         return dx, dx
 
     def _backward_impl(self, st: _Saved, dfeats: Tensor) -> None:
@@ -400,27 +419,42 @@ class VisionTransformer(nn.Module):
         M = B * N
         dev = dfeats.device
         dcls, _ = self._ln_bwd(dfeats.float().contiguous(), st.cls_rows, self.norm, st.meanf, st.rstdf, None, False)
-        dx = torch.zeros((M, D), device=dev, dtype=torch.float32)
-        dx.view(B, N, D)[:, 0] = dcls
         last_s2 = st.blocks[-1][-1]
-        if last_s2 is not None:  # the last block's MLP branch carried a stochastic-depth factor
-            dyf = dx.clone()
-            dyf.view(B, N, D)[:, 0] *= last_s2.view(B, 1)
+        if st.cls_only:
+            # the last block's token-wise tail ran on the cls rows only: so does its backward
+            dx = dcls
+            dyf = dcls * last_s2.view(B, 1) if last_s2 is not None else dcls
             dy = _to_bf16(dyf) if lp else dyf
         else:
-            dy = _to_bf16(dx) if lp else dx
+            dx = torch.zeros((M, D), device=dev, dtype=torch.float32)
+            dx.view(B, N, D)[:, 0] = dcls
+            if last_s2 is not None:  # the last block's MLP branch carried a stochastic-depth factor
+                dyf = dx.clone()
+                dyf.view(B, N, D)[:, 0] *= last_s2.view(B, 1)
+                dy = _to_bf16(dyf) if lp else dyf
+            else:
+                dy = _to_bf16(dx) if lp else dx
 
         nblk = len(st.blocks)
         for i in range(nblk - 1, -1, -1):
             blk = self.blocks[i]
             (x, h, mean1, rstd1, qkv, o, aux, x1, h2, mean2, rstd2, u, a, s1, s2) = st.blocks[i]
             prev_s2 = st.blocks[i - 1][-1] if i > 0 else None
+            cls_only = st.cls_only and i == nblk - 1
             # MLP branch: x2 = x1 + s2 * fc2(gelu(fc1(LN2(x1))))   (dy already carries s2)
             du = self._linear_bwd(dy, a, blk.mlp.fc2, lp, True, dgelu_aux=u)
             dh2 = self._linear_bwd(du, h2, blk.mlp.fc1, lp, True)
-            dx1, dy1 = self._ln_bwd(dh2, x1, blk.norm2, mean2, rstd2, dx, lp, branch_scale=s1)
+            dx1, dy1 = self._ln_bwd(dh2, x1, blk.norm2, mean2, rstd2, dx, lp, branch_scale=s1,
+                                    rows_per_sample=1 if cls_only else None)
             # attention branch: x1 = x + s1 * proj(attn(qkv(LN1(x))))
-            do = self._linear_bwd(dy1, o, blk.attn.proj, lp, True)
+            o_in = o.view(B, N, D)[:, 0].contiguous() if cls_only else o
+            do = self._linear_bwd(dy1, o_in, blk.attn.proj, lp, True)
+            if cls_only:  # back to all tokens: gradients of the other rows are exactly zero up to here
+                do_c, dx1_c = do, dx1
+                do = torch.zeros((M, D), device=dev, dtype=do_c.dtype)
+                do.view(B, N, D)[:, 0] = do_c
+                dx1 = torch.zeros((M, D), device=dev, dtype=torch.float32)
+                dx1.view(B, N, D)[:, 0] = dx1_c
             dqkv = self._attention_bwd(qkv, o, do, aux, B, N, lp)
             dh = self._linear_bwd(dqkv, h, blk.attn.qkv, lp, True)
             dx, dy = self._ln_bwd(dh, x, blk.norm1, mean1, rstd1, dx1, lp, branch_scale=prev_s2)

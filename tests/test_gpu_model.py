@@ -66,6 +66,37 @@ def test_fp32_forward_backward_matches_reference_fixture(golden_rgb, golden_mask
     assert torch.equal(logits.argmax(1).cpu(), torch.from_numpy(g["logits"]).argmax(1))
 
 
+def test_cls_only_last_block_is_exact(golden_rgb):
+    """model.cls_only_last_block (opt-in): the last block's proj / LN2 / MLP on the cls rows only. Same
+    logits and parameter gradients as the reference fixture in fp32, and as the dense schedule in bf16
+    with stochastic depth on (same masks through the same seed)."""
+    g = golden_rgb
+    m = _fixture_model(g)
+    m.backbone.cls_only_last_block = True
+    x, y = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["y"]).to(DEV)
+    logits = m(x)["logits"]
+    loss = losses.build_loss(micro_config())(logits, y)
+    loss.backward()
+    assert rel_err(logits, torch.from_numpy(g["logits"])) < 1e-4
+    worst, who = _grad_errs(m, {k[5:]: v for k, v in g.items() if k.startswith("grad/")})
+    assert worst < 1e-4, (who, worst)
+    grads = {}
+    for flag in (False, True):
+        mm = _fixture_model(g)
+        mm.backbone.cls_only_last_block = flag
+        for i, blk in enumerate(mm.backbone.blocks):
+            blk.drop_path_rate = 0.3 * (i + 1) / len(mm.backbone.blocks)
+        torch.manual_seed(7)
+        with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+            lg = mm(x)["logits"]
+            ls = losses.build_loss(micro_config())(lg, y)
+        ls.backward()
+        grads[flag] = (lg.detach().float(), {n: p.grad.detach().clone() for n, p in mm.named_parameters() if p.grad is not None})
+    assert rel_err(grads[True][0], grads[False][0]) < 1e-5
+    for n, gd in grads[False][1].items():
+        assert rel_err(grads[True][1][n], gd) < 2e-3, n  # same kernels on a row subset: only summation order moves
+
+
 def test_two_fused_steps_match_reference_fixture(golden_rgb):
     """clip(1.0) + AdamW over the reference's LLRD groups + EMA, two steps — the fixture was written
     by torch.optim.AdamW / utils.clip_grad_norm / utils.EMA of the reference (make_golden.py)."""
