@@ -657,15 +657,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint8_t* sb = sa + A_STAGE_BYTES;
         if (elect_one()) {
           mbar_expect_tx(&full_bar[stage],
-                         (EPI == FV_EPI_PATCH && p.im2col) ? p.gw * p.ph_per_tile * 64 + BN * 64 : STAGE_BYTES);
+                         (EPI == FV_EPI_PATCH && p.im2col) ? 2 * p.gw * p.ph_per_tile * 64 + BN * 128 : STAGE_BYTES);
           if (EPI == FV_EPI_PATCH && p.im2col) {
-            // one k-block = one pixel row of a patch: 16 fp32 = 64 B (the longest contiguous run an
-            // NCHW image offers a patch), channel kb/16, row kb%16. The box walks (px, -, pw, ph,
-            // image*channel), so the smem rows come out in token order; 64-byte swizzle.
+            // One pixel row of a patch is 16 fp32 = 64 B — the longest contiguous run an NCHW image
+            // offers a patch — so an A box is [tokens x 64 B] (5-D map walking px, -, pw, ph,
+            // image*channel: the smem rows come out in token order; 64-byte swizzle). A stage holds
+            // TWO such pixel rows (k-block pair kb: channel kb/8, rows 2*(kb%8) and +1) in the two 8 KiB
+            // halves of the A slot, and the 32 matching weight columns as ONE [256 x 128 B] box
+            // (consecutive pixel rows are contiguous in the conv weight; 128-byte swizzle): the
+            // kernel is bound by the TMA unit's rate of 64-byte rows, and the weight rows are two
+            // thirds of them (batch 256: 303 us with one 64-byte-row weight box per pixel row, 224 us like this).
             const int img = m_blk / p.tiles_per_img;
             const int ph0 = (m_blk - img * p.tiles_per_img) * p.ph_per_tile;
-            tma_load_5d(sa, &tmap_a, &full_bar[stage], 0, kb & 15, 0, ph0, img * p.chans + (kb >> 4));
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * 16, n_blk * BN);
+            const int py = (kb & 7) * 2, ch = img * p.chans + (kb >> 3);
+            tma_load_5d(sa, &tmap_a, &full_bar[stage], 0, py, 0, ph0, ch);
+            tma_load_5d(sa + A_STAGE_BYTES / 2, &tmap_a, &full_bar[stage], 0, py + 1, 0, ph0, ch);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * 32, n_blk * BN);
           } else {
             if (p.a_major == FV_MAJOR_K) {
               tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
@@ -717,12 +724,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint64_t da = make_smem_desc_sw128(sa, a_lbo, 1024);
         const uint64_t db = make_smem_desc_sw128(sb, b_lbo, 1024);
         if (elect_one()) {
-          if (tf32) {  // 64-byte rows hold 16 fp32: two K = 8 steps, 32 bytes apart
-            const uint64_t da64 = make_smem_desc_sw64(sa, 16, 512);
-            const uint64_t db64 = make_smem_desc_sw64(sb, 16, 512);
+          if (tf32) {
+            // A: two [tokens x 64 B] halves (64-byte swizzle), two K = 8 steps of 32 bytes in each;
+            // B: [256 x 128 B] (128-byte swizzle), the four K = 8 steps 32 bytes apart along the row
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-              umma_tf32(tmem_d, da64 + k * 2, db64 + k * 2, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t da64 = make_smem_desc_sw64(sa + j * (A_STAGE_BYTES / 2), 16, 512);
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_tf32(tmem_d, da64 + k * 2, db + (j * 2 + k) * 2, idesc, (kb > kb0 || j > 0 || k > 0) ? 1u : 0u);
+            }
           } else {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
@@ -1399,7 +1410,7 @@ extern "C" int fv_patch_embed_tf32(const float* img, const float* weight, const 
   p.K = static_cast<int>(chans * 256);
   p.num_m_blocks = static_cast<int>(batch) * p.tiles_per_img;
   p.num_n_blocks = static_cast<int>(ceil_div(dim, BN));
-  p.num_k_blocks = static_cast<int>(chans) * 16;
+  p.num_k_blocks = static_cast<int>(chans) * 8;  // pairs of pixel rows
   p.split_k = 1;
   p.kb_per_split = p.num_k_blocks;
   p.a_major = FV_MAJOR_K;
@@ -1434,13 +1445,13 @@ extern "C" int fv_patch_embed_tf32(const float* img, const float* weight, const 
       return FV_ERR_CUDA;
     }
   }
-  {  // conv weight [dim, chans*256] fp32, K-major; 16 fp32 = one 64-byte swizzle row
+  {  // conv weight [dim, chans*256] fp32, K-major; 32 fp32 (two pixel rows) = one 128-byte swizzle row
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(chans * 256), static_cast<cuuint64_t>(dim)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(chans) * 256 * 4};
-    cuuint32_t box[2] = {16, BN};
+    cuuint32_t box[2] = {32, BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(weight), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(patch weight) failed (%d)", static_cast<int>(r));
