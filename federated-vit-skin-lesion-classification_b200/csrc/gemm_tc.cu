@@ -664,9 +664,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // image*channel: the smem rows come out in token order; 64-byte swizzle). A stage holds
             // TWO such pixel rows (k-block pair kb: channel kb/8, rows 2*(kb%8) and +1) in the two 8 KiB
             // halves of the A slot, and the 32 matching weight columns as ONE [256 x 128 B] box
-            // (consecutive pixel rows are contiguous in the conv weight; 128-byte swizzle): the
-            // kernel is bound by the TMA unit's rate of 64-byte rows, and the weight rows are two
-            // thirds of them (batch 256: 303 us with one 64-byte-row weight box per pixel row, 224 us like this).
+            // (consecutive pixel rows are contiguous in the conv weight; 128-byte swizzle): half the
+            // stage hand-shakes and a third fewer 64-byte TMA rows (batch 256, timed alone: 231 -> 224 us
+            // with 3 input channels, 251 -> 235 us with 4).
             const int img = m_blk / p.tiles_per_img;
             const int ph0 = (m_blk - img * p.tiles_per_img) * p.ph_per_tile;
             const int py = (kb & 7) * 2, ch = img * p.chans + (kb >> 3);
