@@ -1,7 +1,7 @@
 """Pin the oracle (CPU restatement) before anything is compared against it:
   * against fixtures produced by the reference's own model.py / losses.py / utils.py,
   * against the live reference where /root/reference is mounted (build container),
-  * the timm-ViT restatement against torchvision's independent VisionTransformer.
+  * the timm-ViT restatement against torchvision's and Hugging Face's independent ViT implementations.
 No GPU needed."""
 import numpy as np
 import pytest
@@ -123,6 +123,52 @@ def test_timm_restatement_matches_torchvision_vit():
         ref.heads = torch.nn.Identity()
         x = torch.randn(2, 3, 224, 224)
         assert rel_err(ours(x), ref(x)) < 1e-5
+
+
+def test_timm_restatement_matches_huggingface_vit():
+    """Second independent witness for the absent timm package: Hugging Face's ViTModel (separate q / k / v
+    Linears, its own attention and pooling code) with the restatement's weights — features and the
+    gradient of a scalar of them with respect to the input agree."""
+    tf = pytest.importorskip("transformers")
+    torch.manual_seed(11)
+    ours = create_model("vit_tiny_patch16_224", num_classes=0).eval()
+    D, L, H = 192, 12, 3
+    cfg = tf.ViTConfig(hidden_size=D, num_hidden_layers=L, num_attention_heads=H, intermediate_size=4 * D,
+                       hidden_act="gelu", layer_norm_eps=1e-6, image_size=224, patch_size=16, num_channels=3,
+                       qkv_bias=True, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    ref = tf.ViTModel(cfg, add_pooling_layer=False).eval()
+    with torch.no_grad():
+        for p in ours.parameters():  # non-trivial biases / norms
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.05)
+        sd = ours.state_dict()
+        emb = ref.embeddings
+        emb.cls_token.copy_(sd["cls_token"])
+        emb.position_embeddings.copy_(sd["pos_embed"])
+        emb.patch_embeddings.projection.weight.copy_(sd["patch_embed.proj.weight"])
+        emb.patch_embeddings.projection.bias.copy_(sd["patch_embed.proj.bias"])
+        for i, lyr in enumerate(ref.encoder.layer):
+            p = f"blocks.{i}."
+            lyr.layernorm_before.weight.copy_(sd[p + "norm1.weight"]); lyr.layernorm_before.bias.copy_(sd[p + "norm1.bias"])
+            att = lyr.attention.attention
+            for j, lin in enumerate((att.query, att.key, att.value)):
+                lin.weight.copy_(sd[p + "attn.qkv.weight"][j * D:(j + 1) * D])
+                lin.bias.copy_(sd[p + "attn.qkv.bias"][j * D:(j + 1) * D])
+            lyr.attention.output.dense.weight.copy_(sd[p + "attn.proj.weight"])
+            lyr.attention.output.dense.bias.copy_(sd[p + "attn.proj.bias"])
+            lyr.layernorm_after.weight.copy_(sd[p + "norm2.weight"]); lyr.layernorm_after.bias.copy_(sd[p + "norm2.bias"])
+            lyr.intermediate.dense.weight.copy_(sd[p + "mlp.fc1.weight"]); lyr.intermediate.dense.bias.copy_(sd[p + "mlp.fc1.bias"])
+            lyr.output.dense.weight.copy_(sd[p + "mlp.fc2.weight"]); lyr.output.dense.bias.copy_(sd[p + "mlp.fc2.bias"])
+        ref.layernorm.weight.copy_(sd["norm.weight"]); ref.layernorm.bias.copy_(sd["norm.bias"])
+    x1 = torch.randn(2, 3, 224, 224, requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    f1 = ours(x1)
+    f2 = ref(pixel_values=x2).last_hidden_state[:, 0]
+    assert rel_err(f1, f2) < 1e-5
+    w = torch.randn_like(f1)
+    (f1 * w).sum().backward()
+    (f2 * w).sum().backward()
+    assert rel_err(x1.grad, x2.grad) < 1e-4
 
 
 def test_timm_restatement_shapes_and_counts():
