@@ -401,13 +401,6 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-// same with cluster-scope release: the arriving thread hands over data it observed in ITS CTA's
-// shared memory (a landed TMA tile) to a waiter in the leader CTA
-__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
-               : "memory");
-}
-
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (one row per thread)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
