@@ -64,8 +64,12 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
              const float* __restrict__ seg_lr, const float* __restrict__ seg_wd, int nseg,
              const float* __restrict__ sumsq, float max_norm, float beta1, float beta2, float eps,
              float bc1, float bc2_sqrt, float* __restrict__ ema, float ema_decay,
-             __nv_bfloat16* __restrict__ p_lp, long long nvec) {
+             __nv_bfloat16* __restrict__ p_lp, long long nvec, const float* __restrict__ bc_dev) {
   pdl_wait();
+  if (bc_dev != nullptr) {  // captured in a CUDA graph: the step-dependent bias corrections live in device memory
+    bc1 = __ldg(bc_dev);
+    bc2_sqrt = __ldg(bc_dev + 1);
+  }
   __shared__ long long s_end[MAX_SEGMENTS];
   __shared__ float s_lr[MAX_SEGMENTS];
   __shared__ float s_wd[MAX_SEGMENTS];
@@ -215,22 +219,26 @@ extern "C" int fv_sumsq(const float* g, int64_t n, float* sumsq, int accumulate,
   return FV_OK;
 }
 
-extern "C" int fv_adamw_flat(float* p, const float* g, float* m, float* v, const int64_t* seg_end,
-                             const float* seg_lr, const float* seg_wd, int nseg, const float* sumsq,
-                             float max_norm, float beta1, float beta2, float eps, int64_t step,
-                             float* ema, float ema_decay, void* p_lp, int64_t n, void* stream) {
-  using namespace fv;
+namespace fv {
+static int adamw_flat_impl(float* p, const float* g, float* m, float* v, const int64_t* seg_end,
+                           const float* seg_lr, const float* seg_wd, int nseg, const float* sumsq,
+                           float max_norm, float beta1, float beta2, float eps, int64_t step,
+                           const float* bias_corr, float* ema, float ema_decay, void* p_lp, int64_t n,
+                           void* stream) {
   FV_CHECK_ARG(p && g && m && v && seg_end && seg_lr && seg_wd, "fv_adamw_flat: null pointer");
   FV_CHECK_ARG(nseg > 0 && nseg <= MAX_SEGMENTS, "fv_adamw_flat: nseg=%d out of range", nseg);
   FV_CHECK_ARG(n > 0 && n % 4 == 0, "fv_adamw_flat: n=%lld must be a positive multiple of 4", (long long)n);
-  FV_CHECK_ARG(step >= 1, "fv_adamw_flat: step must be >= 1");
+  FV_CHECK_ARG(bias_corr != nullptr || step >= 1, "fv_adamw_flat: step must be >= 1");
   FV_CHECK_ARG(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) &&
                    (!ema || aligned16(ema)) && (!p_lp || (reinterpret_cast<uintptr_t>(p_lp) & 7) == 0),
                "fv_adamw_flat: arenas must be 16-byte aligned");
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
-  const float fbc1 = static_cast<float>(bc1);
-  const float fbc2s = static_cast<float>(sqrt(bc2));
+  float fbc1 = 1.f, fbc2s = 1.f;
+  if (bias_corr == nullptr) {
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+    fbc1 = static_cast<float>(bc1);
+    fbc2s = static_cast<float>(sqrt(bc2));
+  }
   const long long nvec = n >> 2;
   const unsigned grid = sweep_grid(nvec, 2);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -239,7 +247,7 @@ extern "C" int fv_adamw_flat(float* p, const float* g, float* m, float* v, const
 #define FV_ADAM_LAUNCH(E, L)                                                                      \
   FV_CHECK_CUDA(fv::launch_pdl(adamw_kernel<E, L>, dim3(grid), dim3(SWEEP_THREADS), 0, st, p, g, m, v, se, seg_lr, seg_wd, nseg, sumsq, \
                                                      max_norm, beta1, beta2, eps, fbc1, fbc2s,   \
-                                                     ema, ema_decay, lp, nvec))
+                                                     ema, ema_decay, lp, nvec, bias_corr))
   if (ema && lp) FV_ADAM_LAUNCH(true, true);
   else if (ema) FV_ADAM_LAUNCH(true, false);
   else if (lp) FV_ADAM_LAUNCH(false, true);
@@ -247,6 +255,26 @@ extern "C" int fv_adamw_flat(float* p, const float* g, float* m, float* v, const
 #undef FV_ADAM_LAUNCH
   FV_LAUNCH_CHECK();
   return FV_OK;
+}
+}  // namespace fv
+
+extern "C" int fv_adamw_flat(float* p, const float* g, float* m, float* v, const int64_t* seg_end,
+                             const float* seg_lr, const float* seg_wd, int nseg, const float* sumsq,
+                             float max_norm, float beta1, float beta2, float eps, int64_t step,
+                             float* ema, float ema_decay, void* p_lp, int64_t n, void* stream) {
+  return fv::adamw_flat_impl(p, g, m, v, seg_end, seg_lr, seg_wd, nseg, sumsq, max_norm, beta1, beta2, eps, step,
+                             nullptr, ema, ema_decay, p_lp, n, stream);
+}
+
+// Same sweep with the two step-dependent scalars read from device memory — bias_corr[0] = 1 - beta1^t,
+// bias_corr[1] = sqrt(1 - beta2^t) — so a launch captured in a CUDA graph stays valid for every step t.
+extern "C" int fv_adamw_flat_dev(float* p, const float* g, float* m, float* v, const int64_t* seg_end,
+                                 const float* seg_lr, const float* seg_wd, int nseg, const float* sumsq,
+                                 float max_norm, float beta1, float beta2, float eps, const float* bias_corr,
+                                 float* ema, float ema_decay, void* p_lp, int64_t n, void* stream) {
+  FV_CHECK_ARG(bias_corr != nullptr, "fv_adamw_flat_dev: bias_corr is NULL");
+  return fv::adamw_flat_impl(p, g, m, v, seg_end, seg_lr, seg_wd, nseg, sumsq, max_norm, beta1, beta2, eps, 0,
+                             bias_corr, ema, ema_decay, p_lp, n, stream);
 }
 
 extern "C" int fv_scale_inplace(float* x, const float* sumsq, float max_norm, int64_t n, void* stream) {

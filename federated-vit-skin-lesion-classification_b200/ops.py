@@ -448,6 +448,22 @@ def adamw_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_
              p.numel(), _stream(p))
 
 
+@torch.library.custom_op("fedvit::adamw_flat_dev", mutates_args=("p", "m", "v", "ema", "p_lp"))
+def adamw_flat_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_lr: Tensor,
+                   seg_wd: Tensor, sumsq_: Optional[Tensor], max_norm: float, beta1: float, beta2: float,
+                   eps: float, bias_corr: Tensor, ema: Optional[Tensor], ema_decay: float,
+                   p_lp: Optional[Tensor]) -> None:
+    """``adamw_flat`` with the step-dependent bias corrections ``[1 - beta1^t, sqrt(1 - beta2^t)]`` in a
+    device tensor instead of the step number as a launch argument (CUDA-graph replay)."""
+    _need_cuda(p, g, m, v, seg_end, seg_lr, seg_wd, sumsq_, bias_corr, ema, p_lp)
+    if bias_corr.dtype != torch.float32 or bias_corr.numel() < 2:
+        raise FedVitError("adamw_flat_dev: bias_corr must be fp32 with two entries")
+    LIB.call("fv_adamw_flat_dev", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+             seg_end.data_ptr(), seg_lr.data_ptr(), seg_wd.data_ptr(), seg_end.numel(),
+             _ptr(sumsq_), max_norm, beta1, beta2, eps, bias_corr.data_ptr(), _ptr(ema), ema_decay,
+             _ptr(p_lp), p.numel(), _stream(p))
+
+
 @torch.library.custom_op("fedvit::scale_by_clip", mutates_args=("x",))
 def scale_by_clip(x: Tensor, sumsq_: Tensor, max_norm: float) -> None:
     _need_cuda(x, sumsq_)

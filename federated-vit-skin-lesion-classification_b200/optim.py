@@ -54,6 +54,37 @@ class FusedAdamW(torch.optim.Optimizer):
         self._pending_clip = None  # (sumsq device scalar, max_norm) from utils.clip_grad_norm
         self._seg_key = None
         self._seg = None
+        # CUDA-graph mode (graphs.GraphedTrainStep): the bias corrections of the current step live in a
+        # device tensor that graph_tick() refreshes before every replay
+        self._bias_corr = None      # device fp32 [2]
+        self._bias_corr_host = None  # pinned ring the refresh copies from
+        self._tick_pending = False   # graph_tick() ran and no step has consumed it yet
+
+    # -- CUDA-graph support ---------------------------------------------------------------------------
+    def enable_graph_mode(self) -> None:
+        """From now on ``step()`` launches the sweep variant that reads the step-dependent scalars from
+        device memory. ``graph_tick()`` advances the step (count, bias corrections, lr table): a graph
+        replay needs it called first (GraphedTrainStep does); an eager ``step()`` calls it itself unless
+        the caller already has. The per-group lr / weight-decay table is updated in place when a scheduler
+        changes it, so its device addresses stay valid inside a captured graph."""
+        if self._bias_corr is None:
+            self._bias_corr = torch.ones(2, device=self.arena.device, dtype=torch.float32)
+            self._bias_corr_host = torch.ones((8, 2), dtype=torch.float32).pin_memory()
+            self._segments()
+
+    def graph_tick(self) -> None:
+        """Advance to the next optimisation step: step count, bias corrections -> device, and the lr table
+        if a scheduler moved it. Stream-ordered, no host sync (the pinned slot is reused 8 steps later)."""
+        if self._bias_corr is None:
+            raise RuntimeError("graph_tick() needs enable_graph_mode()")
+        self.step_count += 1
+        b1, b2 = self.defaults["betas"]
+        slot = self._bias_corr_host[self.step_count % 8]
+        slot[0] = 1.0 - b1 ** self.step_count
+        slot[1] = (1.0 - b2 ** self.step_count) ** 0.5
+        self._bias_corr.copy_(slot, non_blocking=True)
+        self._segments()
+        self._tick_pending = True
 
     # -- hooks used by utils.clip_grad_norm / utils.EMA -------------------------------------------
     def defer_clip(self, sumsq: torch.Tensor, max_norm: float) -> None:
@@ -66,9 +97,14 @@ class FusedAdamW(torch.optim.Optimizer):
         if key != self._seg_key:
             ends, lrs, wds = self.arena.segments(self.param_groups)
             dev = self.arena.device
-            self._seg = (torch.tensor(ends, device=dev, dtype=torch.int64),
-                         torch.tensor(lrs, device=dev, dtype=torch.float32),
-                         torch.tensor(wds, device=dev, dtype=torch.float32))
+            new = (torch.tensor(ends, device=dev, dtype=torch.int64),
+                   torch.tensor(lrs, device=dev, dtype=torch.float32),
+                   torch.tensor(wds, device=dev, dtype=torch.float32))
+            if self._bias_corr is not None and self._seg is not None and self._seg[0].numel() == new[0].numel():
+                for old_t, new_t in zip(self._seg, new):  # graph mode: same device addresses
+                    old_t.copy_(new_t)
+            else:
+                self._seg = new
             self._seg_key = key
         return self._seg
 
@@ -93,15 +129,25 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         self._gather_foreign_grads()
         seg_end, seg_lr, seg_wd = self._segments()
-        self.step_count += 1
         b1, b2 = self.defaults["betas"]
         sumsq, max_norm = self._pending_clip if self._pending_clip is not None else (None, 0.0)
         self._pending_clip = None
         ema = self.ema
         a = self.arena
-        ops.adamw_flat(a.params, a.grads, self.exp_avg, self.exp_avg_sq, seg_end, seg_lr, seg_wd,
-                       sumsq, max_norm, b1, b2, self.defaults["eps"], self.step_count,
-                       ema.flat if ema is not None else None, ema.decay if ema is not None else 0.0, a.lp)
+        if self._bias_corr is not None:  # graph mode: graph_tick() advances the step
+            if not torch.cuda.is_current_stream_capturing():
+                if not self._tick_pending:
+                    self.graph_tick()
+                    seg_end, seg_lr, seg_wd = self._seg
+                self._tick_pending = False
+            ops.adamw_flat_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, seg_end, seg_lr, seg_wd,
+                               sumsq, max_norm, b1, b2, self.defaults["eps"], self._bias_corr,
+                               ema.flat if ema is not None else None, ema.decay if ema is not None else 0.0, a.lp)
+        else:
+            self.step_count += 1
+            ops.adamw_flat(a.params, a.grads, self.exp_avg, self.exp_avg_sq, seg_end, seg_lr, seg_wd,
+                           sumsq, max_norm, b1, b2, self.defaults["eps"], self.step_count,
+                           ema.flat if ema is not None else None, ema.decay if ema is not None else 0.0, a.lp)
         if a.lp is not None:
             a.mark_lp_fresh()
         if ema is not None:

@@ -226,6 +226,14 @@ int fv_adamw_flat(float* p, const float* g, float* m, float* v,
                   const float* sumsq, float max_norm, float beta1, float beta2, float eps,
                   int64_t step, float* ema, float ema_decay, void* p_lp,
                   int64_t n, void* stream);
+/* The same sweep with the two step-dependent scalars in DEVICE memory — bias_corr[0] = 1 - beta1^t,
+ * bias_corr[1] = sqrt(1 - beta2^t), written by the host before each step — so a launch captured in a
+ * CUDA graph (fedvit_b200.graphs.GraphedTrainStep) replays correctly for every step t. */
+int fv_adamw_flat_dev(float* p, const float* g, float* m, float* v,
+                      const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int nseg,
+                      const float* sumsq, float max_norm, float beta1, float beta2, float eps,
+                      const float* bias_corr, float* ema, float ema_decay, void* p_lp,
+                      int64_t n, void* stream);
 int fv_scale_inplace(float* x, const float* sumsq, float max_norm, int64_t n, void* stream);
 int fv_ema_update(float* shadow, const float* p, float decay, int64_t n, void* stream);
 int fv_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -241,6 +241,94 @@ def test_train_one_epoch_matches_oracle_local_epoch(golden_rgb):
     assert rel_err(m2.classifier[0].weight, ora2.classifier[0].weight) < POST_ADAM_TOL
 
 
+def test_graphed_train_step_matches_eager_steps(golden_rgb):
+    """graphs.GraphedTrainStep (zero_grad + forward + loss + backward + clip + fused AdamW + EMA as ONE
+    CUDA graph, bias corrections read from device memory) against the same steps run eagerly: same
+    parameters, EMA shadow and losses over 3 steps (construction rolls its warm-up steps back); a scheduler-style lr change between
+    replays lands in the captured launch through the in-place lr table."""
+    g = golden_rgb
+    x, y = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["y"]).to(DEV)
+    x2 = x.flip(0).contiguous()
+    from fedvit_b200 import graphs
+
+    crit = losses.build_loss(micro_config())
+
+    def fresh():
+        m = _fixture_model(g)
+        opt = optim.FusedAdamW(model.get_layerwise_lr_groups(m, 1e-3, 0.75, 1e-2), weight_decay=1e-2, arena=FlatArena(m))
+        ema = utils.EMA(m, decay=0.9).attach(opt)
+        return m, opt, ema
+
+    m1, o1, e1 = fresh()
+    m2, o2, e2 = fresh()
+    batches = [(x, y), (x2, y), (x, y)]
+    losses_eager = []
+    for i, (bx, by) in enumerate(batches):
+        if i == 2:
+            for grp in o1.param_groups:
+                grp["lr"] *= 0.5
+        o1.zero_grad(set_to_none=True)
+        with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+            ls = crit(m1(bx)["logits"], by)
+        ls.backward()
+        utils.clip_grad_norm(m1.parameters(), 1.0, optimizer=o1)
+        o1.step()
+        e1.update()
+        losses_eager.append(float(ls.detach()))
+    before = o2.arena.params.clone()
+    step = graphs.GraphedTrainStep(m2, crit, o2, x, y, grad_clip=1.0)  # warm-up steps are rolled back
+    assert o2.step_count == 0 and torch.equal(o2.arena.params, before)
+    got = []
+    for i, (bx, by) in enumerate(batches):
+        if i == 2:
+            for grp in o2.param_groups:
+                grp["lr"] *= 0.5
+        got.append(float(step(bx, by)))
+        e2.update()
+    assert o2.step_count == o1.step_count == 3
+    assert got == pytest.approx(losses_eager, rel=POST_ADAM_TOL)
+    for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if n.endswith("attn.qkv.bias"):
+            # the key-bias gradient is mathematically zero: what Adam steps on is the rounding noise of the
+            # atomically summed column sums, different in any two runs — compare the q and v thirds
+            d = p1.numel() // 3
+            p1, p2 = torch.cat([p1[:d], p1[2 * d:]]), torch.cat([p2[:d], p2[2 * d:]])
+        assert rel_err(p2, p1) < POST_ADAM_TOL, n  # same kernels; only the order of atomic adds may differ
+    assert rel_err(e2.shadow["backbone.norm.weight"], e1.shadow["backbone.norm.weight"]) < POST_ADAM_TOL
+    # an eager step after the replays keeps counting (graph mode ticks inside step())
+    o2.zero_grad(set_to_none=True)
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        crit(m2(x)["logits"], y).backward()
+    o2.step()
+    assert o2.step_count == 4
+
+
+def test_train_one_epoch_with_cuda_graph_matches_eager_epoch(golden_rgb):
+    """training.cuda_graph: the epoch loop replays the captured step; same epoch loss and parameters as the
+    eager loop, twice in a row (the graph is cached on the model across epochs)."""
+    loader = data.SyntheticClientLoader(0, 24, 6, 32, channels=3, num_classes=7, pin=False)
+    out = {}
+    for flag in (False, True):
+        cfg = micro_config()
+        cfg["training"]["use_amp"] = True
+        cfg["training"]["cuda_graph"] = flag
+        m = _fixture_model(golden_rgb)
+        opt = optim.FusedAdamW(model.get_layerwise_lr_groups(m, 1e-3, 0.75, 1e-2), weight_decay=1e-2, arena=FlatArena(m))
+        crit = losses.build_loss(cfg)
+        l0 = train.train_one_epoch(m, loader, crit, opt, None, None, None, DEV, cfg, 0, None)
+        l1 = train.train_one_epoch(m, loader, crit, opt, None, None, None, DEV, cfg, 1, None)
+        assert opt.step_count == 2 * len(loader)
+        out[flag] = (l0, l1, {n: p.detach().clone() for n, p in m.named_parameters()})
+    assert out[True][0] == pytest.approx(out[False][0], rel=POST_ADAM_TOL)
+    assert out[True][1] == pytest.approx(out[False][1], rel=5 * POST_ADAM_TOL)
+    for n, p in out[False][2].items():
+        q = out[True][2][n]
+        if n.endswith("attn.qkv.bias"):  # zero-gradient key bias: Adam steps on rounding noise (see above)
+            d = p.numel() // 3
+            p, q = torch.cat([p[:d], p[2 * d:]]), torch.cat([q[:d], q[2 * d:]])
+        assert rel_err(q, p) < 5 * POST_ADAM_TOL, n
+
+
 @pytest.mark.parametrize("lag", [1, 2, 5])
 def test_per_step_loss_readback_matches_device_accumulation(golden_rgb, lag):
     """training.sync_loss_every_step (the reference reads loss.item() every step, train.py:164): the
