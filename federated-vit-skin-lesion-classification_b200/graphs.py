@@ -98,7 +98,6 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         # torch.cuda.graph only records: the step it describes first RUNS at the first replay, so the step
         # count is not advanced here (host-side bookkeeping inside _run happens once, at capture)
-        self._ticked = False
         with torch.cuda.graph(self.graph):
             self.static_loss = self._run()
         if optimizer.ema is not None:  # step() counted a fused EMA update that the capture did not execute
@@ -152,10 +151,12 @@ class GraphedTrainStep:
         self.static_y.copy_(labels, non_blocking=True)
         if self.static_meta is not None and metadata is not None:
             self.static_meta.copy_(metadata, non_blocking=True)
-        if self._ticked:
-            self._ticked = False
-        else:
-            self.optimizer.graph_tick()
+        arena = self.optimizer.arena
+        if arena.lp is not None:
+            # parameters written through PyTorch since the last step (a FedAvg install, a checkpoint load):
+            # the captured forward reads the bf16 shadow as it finds it, so bring it up to date here
+            arena.refresh_lp()
+        self.optimizer.graph_tick()
         self.graph.replay()
         self.optimizer._tick_pending = False  # consumed by the replayed sweep
         if self.optimizer.ema is not None:  # the replayed sweep updated the shadow (utils.EMA.update() then skips)

@@ -295,12 +295,21 @@ def test_graphed_train_step_matches_eager_steps(golden_rgb):
             p1, p2 = torch.cat([p1[:d], p1[2 * d:]]), torch.cat([p2[:d], p2[2 * d:]])
         assert rel_err(p2, p1) < POST_ADAM_TOL, n  # same kernels; only the order of atomic adds may differ
     assert rel_err(e2.shadow["backbone.norm.weight"], e1.shadow["backbone.norm.weight"]) < POST_ADAM_TOL
+    # parameters installed through PyTorch between steps (what a FedAvg round does) reach the captured forward
+    with torch.no_grad():
+        for mm in (m1, m2):
+            for p in mm.parameters():
+                p.mul_(0.5)
+    o1.zero_grad(set_to_none=True)
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        ls = crit(m1(x)["logits"], y)
+    assert float(step(x, y)) == pytest.approx(float(ls.detach()), rel=1e-3)
     # an eager step after the replays keeps counting (graph mode ticks inside step())
     o2.zero_grad(set_to_none=True)
     with torch.amp.autocast("cuda", dtype=torch.bfloat16):
         crit(m2(x)["logits"], y).backward()
     o2.step()
-    assert o2.step_count == 4
+    assert o2.step_count == 5
 
 
 def test_train_one_epoch_with_cuda_graph_matches_eager_epoch(golden_rgb):
