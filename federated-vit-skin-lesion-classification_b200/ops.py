@@ -11,6 +11,8 @@ where the saved-activation lifetime is managed explicitly.
 """
 from __future__ import annotations
 
+import functools
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -21,6 +23,34 @@ from ._lib import LIB, FedVitError
 F32, BF16 = 0, 1
 EPI = {"none": 0, "residual": 1, "gelu": 2, "dgelu": 3, "accum": 4, "patch": 5}
 MAJOR_K, MAJOR_MN = 0, 1
+
+
+class _Op:
+    """Python entry point of one library op. Calling it runs the implementation directly (argument
+    checks + one ctypes call on the current stream). The same function is registered as the
+    ``torch.library`` custom op ``torch.ops.fedvit.<name>`` (``.op``): that is the path for FakeTensor
+    tracing / export, but each trip through the dispatcher costs ~20 us of host time in Python — 5 ms of a
+    250-launch training step, more than the GPU needs for a ViT-Tiny step — so the framework's own callers
+    (vit.py, head.py, losses.py, optim.py) take the direct route. ``FEDVIT_DISPATCH=1`` sends every call
+    through the dispatcher instead (A/B)."""
+
+    def __init__(self, name: str, fn, mutates_args) -> None:
+        self.fn = fn
+        self.op = torch.library.custom_op(name, mutates_args=mutates_args)(fn)
+        self._via_dispatcher = os.environ.get("FEDVIT_DISPATCH", "0") == "1"
+        functools.update_wrapper(self, fn)
+
+    def __call__(self, *args, **kwargs):
+        if self._via_dispatcher:
+            return self.op(*args, **kwargs)
+        return self.fn(*args, **kwargs)
+
+    def register_fake(self, fake):
+        return self.op.register_fake(fake)
+
+
+def _op(name: str, mutates_args):
+    return lambda fn: _Op(name, fn, mutates_args)
 
 
 def _dt(t: Tensor) -> int:
@@ -101,7 +131,7 @@ def _gemm_impl(a, b, bias, out, aux, a_major, b_major, epilogue, split_k, tokens
         )
 
 
-@torch.library.custom_op("fedvit::gemm", mutates_args=("out",))
+@_op("fedvit::gemm", mutates_args=("out",))
 def gemm(
     a: Tensor,
     b: Tensor,
@@ -126,7 +156,7 @@ def gemm(
     _gemm_impl(a, b, bias, out, aux, a_major, b_major, epilogue, split_k, tokens_per_img)
 
 
-@torch.library.custom_op("fedvit::gemm_gelu", mutates_args=("out", "pre"))
+@_op("fedvit::gemm_gelu", mutates_args=("out", "pre"))
 def gemm_gelu(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor, pre: Tensor) -> None:
     """u = a @ b^T + bias ; out = gelu_erf(u) ; pre = gelu_erf'(u)  (fc1 of the MLP).
 
@@ -136,14 +166,14 @@ def gemm_gelu(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor, pre: Te
     _gemm_impl(a, b, bias, out, pre, MAJOR_K, MAJOR_K, EPI["gelu"], 1, 0)
 
 
-@torch.library.custom_op("fedvit::gemm_gelu_fwd", mutates_args=("out",))
+@_op("fedvit::gemm_gelu_fwd", mutates_args=("out",))
 def gemm_gelu_fwd(a: Tensor, b: Tensor, bias: Optional[Tensor], out: Tensor) -> None:
     """out = gelu_erf(a @ b^T + bias) without the derivative output — the forward-only (eval /
     no-grad) form of :func:`gemm_gelu`: half the epilogue's stores."""
     _gemm_impl(a, b, bias, out, None, MAJOR_K, MAJOR_K, EPI["gelu"], 1, 0)
 
 
-@torch.library.custom_op("fedvit::linear_residual", mutates_args=("out",))
+@_op("fedvit::linear_residual", mutates_args=("out",))
 def linear_residual(a: Tensor, w: Tensor, bias: Optional[Tensor], residual: Tensor, row_scale: Optional[Tensor],
                     rows_per_scale: int, out: Tensor) -> None:
     """out = residual + row_scale[row // rows_per_scale] * (a @ w^T + bias) — a block's branch +
@@ -172,7 +202,7 @@ def linear_residual(a: Tensor, w: Tensor, bias: Optional[Tensor], residual: Tens
         trace.append((e0, e1, 2.0 * m * n * k))
 
 
-@torch.library.custom_op("fedvit::wgrad", mutates_args=("dw", "dbias"))
+@_op("fedvit::wgrad", mutates_args=("dw", "dbias"))
 def wgrad(dy: Tensor, x: Tensor, dw: Tensor, dbias: Optional[Tensor], split_k: int) -> None:
     """dw[out,in] += dy^T @ x and dbias[out] += dy.sum(0), bf16 operands, one tensor-core kernel."""
     _need_cuda(dy, x, dw, dbias)
@@ -196,7 +226,7 @@ def wgrad(dy: Tensor, x: Tensor, dw: Tensor, dbias: Optional[Tensor], split_k: i
         trace.append((e0, e1, 2.0 * dy.shape[0] * dy.shape[1] * x.shape[1]))
 
 
-@torch.library.custom_op("fedvit::bgemm_f32", mutates_args=("out",))
+@_op("fedvit::bgemm_f32", mutates_args=("out",))
 def bgemm_f32(
     a: Tensor, a_strides: List[int], b: Tensor, b_strides: List[int], out: Tensor,
     out_strides: List[int], m: int, n: int, k: int, batch: int, alpha: float, accumulate: bool,
@@ -218,7 +248,7 @@ def bgemm_f32(
 # ------------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------------
-@torch.library.custom_op("fedvit::layernorm_fwd", mutates_args=())
+@_op("fedvit::layernorm_fwd", mutates_args=())
 def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, out_bf16: bool) -> Tuple[Tensor, Tensor, Tensor]:
     _need_cuda(x, gamma, beta)
     if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2:
@@ -238,7 +268,7 @@ def _(x, gamma, beta, eps, out_bf16):
     return y, x.new_empty((x.shape[0],)), x.new_empty((x.shape[0],))
 
 
-@torch.library.custom_op("fedvit::layernorm_bwd", mutates_args=("dgamma", "dbeta"))
+@_op("fedvit::layernorm_bwd", mutates_args=("dgamma", "dbeta"))
 def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor,
                   dres: Optional[Tensor], dgamma: Tensor, dbeta: Tensor, want_lp: bool,
                   lp_scale: Optional[Tensor] = None, rows_per_scale: int = 0) -> Tuple[Tensor, Tensor]:
@@ -264,7 +294,7 @@ def _(dy, x, gamma, mean, rstd, dres, dgamma, dbeta, want_lp, lp_scale=None, row
 # ------------------------------------------------------------------------------------------------
 # attention core (bf16 flash kernels)
 # ------------------------------------------------------------------------------------------------
-@torch.library.custom_op("fedvit::attention_fwd", mutates_args=())
+@_op("fedvit::attention_fwd", mutates_args=())
 def attention_fwd(qkv: Tensor, batch: int, tokens: int, heads: int, scale: float) -> Tuple[Tensor, Tensor]:
     """qkv [B*N, 3*H*64] bf16 -> (out [B*N, H*64] bf16, lse [B, H, N] fp32)."""
     _need_cuda(qkv)
@@ -283,7 +313,7 @@ def _(qkv, batch, tokens, heads, scale):
             qkv.new_empty((batch, heads, tokens), dtype=torch.float32))
 
 
-@torch.library.custom_op("fedvit::attention_bwd", mutates_args=())
+@_op("fedvit::attention_bwd", mutates_args=())
 def attention_bwd(qkv: Tensor, out: Tensor, dout: Tensor, lse: Tensor, batch: int, tokens: int,
                   heads: int, scale: float) -> Tensor:
     _need_cuda(qkv, out, dout, lse)
@@ -303,7 +333,7 @@ def _(qkv, out, dout, lse, batch, tokens, heads, scale):
     return torch.empty_like(qkv)
 
 
-@torch.library.custom_op("fedvit::softmax_rows", mutates_args=())
+@_op("fedvit::softmax_rows", mutates_args=())
 def softmax_rows(s: Tensor, scale: float) -> Tensor:
     _need_cuda(s)
     p = torch.empty_like(s)
@@ -317,7 +347,7 @@ def _(s, scale):
     return torch.empty_like(s)
 
 
-@torch.library.custom_op("fedvit::softmax_rows_bwd", mutates_args=())
+@_op("fedvit::softmax_rows_bwd", mutates_args=())
 def softmax_rows_bwd(p: Tensor, dp: Tensor, scale: float) -> Tensor:
     _need_cuda(p, dp)
     ds = torch.empty_like(p)
@@ -335,7 +365,7 @@ def _(p, dp, scale):
 # ------------------------------------------------------------------------------------------------
 # patch embedding helpers, column sums
 # ------------------------------------------------------------------------------------------------
-@torch.library.custom_op("fedvit::patchify", mutates_args=())
+@_op("fedvit::patchify", mutates_args=())
 def patchify(img: Tensor, out_bf16: bool) -> Tensor:
     """NCHW fp32 image -> [B*(H/16)*(W/16), C*256] patch rows, (c, py, px) column order."""
     _need_cuda(img)
@@ -356,7 +386,7 @@ def _(img, out_bf16):
                          dtype=torch.bfloat16 if out_bf16 else torch.float32)
 
 
-@torch.library.custom_op("fedvit::patch_embed", mutates_args=("x",))
+@_op("fedvit::patch_embed", mutates_args=("x",))
 def patch_embed(img: Tensor, weight: Tensor, bias: Tensor, pos: Tensor, x: Tensor) -> None:
     """Rows 1..N-1 of the residual stream from the NCHW fp32 image, im2col-free (5-D TMA, tf32)."""
     _need_cuda(img, weight, bias, pos, x)
@@ -371,13 +401,13 @@ def patch_embed(img: Tensor, weight: Tensor, bias: Tensor, pos: Tensor, x: Tenso
              x.data_ptr(), b, c, h, w, d, _stream(img))
 
 
-@torch.library.custom_op("fedvit::cls_pos_rows", mutates_args=("x",))
+@_op("fedvit::cls_pos_rows", mutates_args=("x",))
 def cls_pos_rows(cls: Tensor, pos: Tensor, x: Tensor, batch: int, tokens: int, dim: int) -> None:
     _need_cuda(cls, pos, x)
     LIB.call("fv_cls_pos_rows", cls.data_ptr(), pos.data_ptr(), x.data_ptr(), batch, tokens, dim, _stream(x))
 
 
-@torch.library.custom_op("fedvit::colsum", mutates_args=("out",))
+@_op("fedvit::colsum", mutates_args=("out",))
 def colsum(a: Tensor, out: Tensor, accumulate: bool) -> None:
     """out[c] (+)= sum_r a[r, c] — bias / pos_embed / cls_token gradients."""
     _need_cuda(a, out)
@@ -390,7 +420,7 @@ def colsum(a: Tensor, out: Tensor, accumulate: bool) -> None:
 # ------------------------------------------------------------------------------------------------
 # losses
 # ------------------------------------------------------------------------------------------------
-@torch.library.custom_op("fedvit::asl_loss", mutates_args=())
+@_op("fedvit::asl_loss", mutates_args=())
 def asl_loss(logits: Tensor, targets: Tensor, gamma_neg: float, gamma_pos: float, clip: float,
              eps: float) -> Tuple[Tensor, Tensor]:
     """(mean asymmetric-focal loss [scalar], d loss / d logits [B,C]) in one fused pass."""
@@ -410,7 +440,7 @@ def _(logits, targets, gamma_neg, gamma_pos, clip, eps):
     return logits.new_empty((), dtype=torch.float32), logits.new_empty(logits.shape, dtype=torch.float32)
 
 
-@torch.library.custom_op("fedvit::ce_loss", mutates_args=())
+@_op("fedvit::ce_loss", mutates_args=())
 def ce_loss(logits: Tensor, targets: Tensor) -> Tuple[Tensor, Tensor]:
     _need_cuda(logits, targets)
     logits = logits.float().contiguous()
@@ -430,13 +460,13 @@ def _(logits, targets):
 # ------------------------------------------------------------------------------------------------
 # flat-arena sweeps: grad norm, AdamW(+EMA+bf16 cast), EMA, FedAvg fold, cast
 # ------------------------------------------------------------------------------------------------
-@torch.library.custom_op("fedvit::sumsq", mutates_args=("out",))
+@_op("fedvit::sumsq", mutates_args=("out",))
 def sumsq(g: Tensor, out: Tensor, accumulate: bool) -> None:
     _need_cuda(g, out)
     LIB.call("fv_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), int(accumulate), _stream(g))
 
 
-@torch.library.custom_op("fedvit::adamw_flat", mutates_args=("p", "m", "v", "ema", "p_lp"))
+@_op("fedvit::adamw_flat", mutates_args=("p", "m", "v", "ema", "p_lp"))
 def adamw_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_lr: Tensor,
                seg_wd: Tensor, sumsq_: Optional[Tensor], max_norm: float, beta1: float, beta2: float,
                eps: float, step: int, ema: Optional[Tensor], ema_decay: float,
@@ -448,7 +478,7 @@ def adamw_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_
              p.numel(), _stream(p))
 
 
-@torch.library.custom_op("fedvit::adamw_flat_dev", mutates_args=("p", "m", "v", "ema", "p_lp"))
+@_op("fedvit::adamw_flat_dev", mutates_args=("p", "m", "v", "ema", "p_lp"))
 def adamw_flat_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_lr: Tensor,
                    seg_wd: Tensor, sumsq_: Optional[Tensor], max_norm: float, beta1: float, beta2: float,
                    eps: float, bias_corr: Tensor, ema: Optional[Tensor], ema_decay: float,
@@ -464,19 +494,19 @@ def adamw_flat_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, 
              _ptr(p_lp), p.numel(), _stream(p))
 
 
-@torch.library.custom_op("fedvit::scale_by_clip", mutates_args=("x",))
+@_op("fedvit::scale_by_clip", mutates_args=("x",))
 def scale_by_clip(x: Tensor, sumsq_: Tensor, max_norm: float) -> None:
     _need_cuda(x, sumsq_)
     LIB.call("fv_scale_inplace", x.data_ptr(), sumsq_.data_ptr(), max_norm, x.numel(), _stream(x))
 
 
-@torch.library.custom_op("fedvit::ema_update", mutates_args=("shadow",))
+@_op("fedvit::ema_update", mutates_args=("shadow",))
 def ema_update(shadow: Tensor, p: Tensor, decay: float) -> None:
     _need_cuda(shadow, p)
     LIB.call("fv_ema_update", shadow.data_ptr(), p.data_ptr(), decay, p.numel(), _stream(p))
 
 
-@torch.library.custom_op("fedvit::fedavg_accum", mutates_args=("acc",))
+@_op("fedvit::fedavg_accum", mutates_args=("acc",))
 def fedavg_accum(acc: Tensor, w: Tensor, weight: float, init: bool) -> None:
     """acc = (init ? 0 : acc) + weight * w over a flat fp32 arena."""
     _need_cuda(acc, w)
@@ -485,7 +515,7 @@ def fedavg_accum(acc: Tensor, w: Tensor, weight: float, init: bool) -> None:
     LIB.call("fv_fedavg_accum", acc.data_ptr(), w.data_ptr(), weight, int(init), w.numel(), _stream(w))
 
 
-@torch.library.custom_op("fedvit::cast_bf16", mutates_args=("dst",))
+@_op("fedvit::cast_bf16", mutates_args=("dst",))
 def cast_bf16(src: Tensor, dst: Tensor) -> None:
     _need_cuda(src, dst)
     LIB.call("fv_cast_f32_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream(src))
@@ -510,7 +540,7 @@ def _mix_args(perm: Optional[Tensor], lam: float, mode: int, box, batch: int):
     return perm, float(lam), float(1.0 - lam), x1, y1, x2, y2
 
 
-@torch.library.custom_op("fedvit::mix_batch", mutates_args=())
+@_op("fedvit::mix_batch", mutates_args=())
 def mix_batch(x: Tensor, perm: Optional[Tensor], lam: float, mode: int, box: List[int]) -> Tensor:
     """MixUp (mode 1: ``lam*x + (1-lam)*x[perm]``) or CutMix (mode 2: rows box[0]:box[2] x columns
     box[1]:box[3] taken from ``x[perm]``) of an fp32 NCHW batch in one pass — reference
@@ -531,7 +561,7 @@ def _(x, perm, lam, mode, box):
     return torch.empty_like(x)
 
 
-@torch.library.custom_op("fedvit::assemble_batch", mutates_args=())
+@_op("fedvit::assemble_batch", mutates_args=())
 def assemble_batch(img_u8: Tensor, mask_u8: Optional[Tensor], mean: List[float], std: List[float],
                    perm: Optional[Tensor], lam: float, mode: int, box: List[int]) -> Tensor:
     """uint8 images ([B,3,H,W] or [B,H,W,3]) + optional uint8 masks [B,H,W] -> normalised fp32 NCHW

@@ -38,6 +38,19 @@ def test_public_names_and_signatures_match_reference():
         assert hasattr(utils, name)
 
 
+def test_ops_are_registered_as_torch_library_custom_ops():
+    """Every Python entry point of the kernel library is also a torch.library custom op (namespace fedvit),
+    the framework's own callers use the direct route (ops._Op)."""
+    import fedvit_b200  # noqa: F401
+    from fedvit_b200 import ops
+
+    names = [n for n, v in vars(ops).items() if isinstance(v, ops._Op)]
+    assert len(names) >= 27 and {"gemm", "wgrad", "layernorm_bwd", "attention_fwd", "adamw_flat_dev", "fedavg_accum"} <= set(names)
+    for n in names:
+        assert hasattr(torch.ops.fedvit, n), n
+        assert callable(getattr(ops, n).fn)
+
+
 def test_state_dict_keys_and_groups_match_oracle(golden_rgb):
     cfg = micro_config()
     ours = model.build_model(cfg)
