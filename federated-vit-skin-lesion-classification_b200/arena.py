@@ -49,6 +49,11 @@ class FlatArena:
         self.grads = torch.zeros(off, device=dev, dtype=torch.float32)
         self.lp = torch.zeros(off, device=dev, dtype=torch.bfloat16) if with_lp else None
         self._lp_versions: Optional[List[int]] = None
+        # per-parameter views of the gradient buffer and the bf16 shadow, made once: every step asks for
+        # each of them several times (zero_grad, clip, the optimiser's foreign-gradient check, the GEMMs'
+        # weight operands), and slicing + reshaping ~150 tensors costs the host about a millisecond a time
+        self._grad_views: Dict[str, torch.Tensor] = {}
+        self._lp_views: Dict[str, torch.Tensor] = {}
         with torch.no_grad():
             for (n, p) in named:
                 o, k = self.offsets[n]
@@ -64,14 +69,20 @@ class FlatArena:
         p = self._params[self._index[name]]
         return buf[o:o + k].view(p.shape)
 
+    def _cached(self, cache: Dict[str, torch.Tensor], buf: torch.Tensor, name: str) -> torch.Tensor:
+        v = cache.get(name)
+        if v is None:
+            v = cache[name] = self.view(buf, name)
+        return v
+
     def grad_view(self, p: nn.Parameter) -> torch.Tensor:
-        return self.view(self.grads, p._fv_arena[1])
+        return self._cached(self._grad_views, self.grads, p._fv_arena[1])
 
     def attach_grads(self) -> None:
         """Point every ``p.grad`` at its slice of the gradient buffer (requires_grad params only)."""
         for n, p in zip(self.names, self._params):
             if p.requires_grad:
-                p.grad = self.view(self.grads, n)
+                p.grad = self._cached(self._grad_views, self.grads, n)
 
     def zero_grads(self) -> None:
         self.grads.zero_()
@@ -107,7 +118,7 @@ class FlatArena:
             self.mark_lp_fresh()
 
     def lp_view(self, p: nn.Parameter) -> torch.Tensor:
-        return self.view(self.lp, p._fv_arena[1])
+        return self._cached(self._lp_views, self.lp, p._fv_arena[1])
 
     # ------------------------------------------------------------------------------------------
     def segments(self, param_groups: Iterable[dict]) -> Tuple[List[int], List[float], List[float]]:
