@@ -121,28 +121,36 @@ class FlatArena:
         return self._cached(self._lp_views, self.lp, p._fv_arena[1])
 
     # ------------------------------------------------------------------------------------------
-    def segments(self, param_groups: Iterable[dict]) -> Tuple[List[int], List[float], List[float]]:
+    def segments(self, param_groups: Iterable[dict], by_group: bool = False) -> Tuple[List[int], List[float], List[float]]:
         """(end offsets, lr, weight_decay) per arena range; lr = -1 marks parameters that belong to
         no optimiser group (reference quirk: cls_token / pos_embed, model.py:228-270). Adjacent
-        ranges with identical hyper-parameters are merged."""
+        ranges with identical hyper-parameters are merged — or, with ``by_group``, adjacent ranges of the
+        same param group whatever their values: the table then keeps its length when a scheduler moves
+        the learning rates (a captured CUDA graph holds the table's device addresses)."""
         hp: Dict[int, Tuple[float, float]] = {}
-        for g in param_groups:
+        gid: Dict[int, int] = {}
+        for gi, g in enumerate(param_groups):
             for p in g["params"]:
                 hp[id(p)] = (float(g["lr"]), float(g["weight_decay"]))
+                gid[id(p)] = gi
         ends: List[int] = []
         lrs: List[float] = []
         wds: List[float] = []
+        last_key = None
         for i, (n, p) in enumerate(zip(self.names, self._params)):
             nxt = self.offsets[self.names[i + 1]][0] if i + 1 < len(self.names) else self.numel
             lr, wd = hp.get(id(p), (-1.0, 0.0))
+            g = gid.get(id(p), -1)
             if not p.requires_grad:
-                lr, wd = -1.0, 0.0
-            if ends and lrs[-1] == lr and wds[-1] == wd:
+                lr, wd, g = -1.0, 0.0, -1
+            key = g if by_group else (lr, wd)
+            if ends and key == last_key:
                 ends[-1] = nxt
             else:
                 ends.append(nxt)
                 lrs.append(lr)
                 wds.append(wd)
+            last_key = key
         return ends, lrs, wds
 
 

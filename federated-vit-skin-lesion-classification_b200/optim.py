@@ -70,6 +70,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._bias_corr is None:
             self._bias_corr = torch.ones(2, device=self.arena.device, dtype=torch.float32)
             self._bias_corr_host = torch.ones((8, 2), dtype=torch.float32).pin_memory()
+            self._seg_key, self._seg = None, None  # rebuilt per param group: fixed length from here on
             self._segments()
 
     def graph_tick(self) -> None:
@@ -95,13 +96,16 @@ class FusedAdamW(torch.optim.Optimizer):
     def _segments(self):
         key = tuple((float(g["lr"]), float(g["weight_decay"])) for g in self.param_groups)
         if key != self._seg_key:
-            ends, lrs, wds = self.arena.segments(self.param_groups)
+            ends, lrs, wds = self.arena.segments(self.param_groups, by_group=self._bias_corr is not None)
             dev = self.arena.device
             new = (torch.tensor(ends, device=dev, dtype=torch.int64),
                    torch.tensor(lrs, device=dev, dtype=torch.float32),
                    torch.tensor(wds, device=dev, dtype=torch.float32))
-            if self._bias_corr is not None and self._seg is not None and self._seg[0].numel() == new[0].numel():
-                for old_t, new_t in zip(self._seg, new):  # graph mode: same device addresses
+            if self._bias_corr is not None and self._seg is not None:
+                if self._seg[0].numel() != new[0].numel():
+                    raise RuntimeError("FusedAdamW (graph mode): the param-group layout changed after "
+                                       "enable_graph_mode() — build a new GraphedTrainStep")
+                for old_t, new_t in zip(self._seg, new):  # same device addresses for the captured launch
                     old_t.copy_(new_t)
             else:
                 self._seg = new

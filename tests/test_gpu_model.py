@@ -564,6 +564,28 @@ def test_config1_vit_tiny_fedavg_round_fp32_vs_oracle():
     assert out["rounds"][0]["mean_client_loss"] == pytest.approx(loss, rel=0.2)
 
 
+def test_federated_rounds_with_opt_in_modes_match_default():
+    """run_federated (3 clients, 2 rounds, bf16, EMA, cosine schedule) with training.cuda_graph and
+    model.cls_only_last_block on against the default schedule: same global model. Exercises the captured
+    step across clients and rounds — optimiser reset, global weights installed through PyTorch, lr changed
+    by the scheduler between rounds."""
+    outs = {}
+    for flag in (False, True):
+        cfg = micro_config()
+        cfg["model"]["cls_only_last_block"] = flag
+        cfg["training"].update({"use_amp": True, "cuda_graph": flag, "batch_size": 6,
+                                "scheduler": {"warmup_epochs": 1, "min_lr": 1e-5}, "ema": {"enabled": True, "decay": 0.9}})
+        cfg["federated"] = {"num_clients": 3, "rounds": 2, "local_epochs": 1, "samples_per_client": 24}
+        outs[flag] = train.run_federated(cfg, device=DEV)
+    a, b = outs[True], outs[False]
+    for r1, r2 in zip(a["rounds"], b["rounds"]):
+        assert r1["mean_client_loss"] == pytest.approx(r2["mean_client_loss"], rel=1e-2)
+    probe = torch.randn(6, 3, 32, 32, generator=torch.Generator().manual_seed(5)).to(DEV)
+    with torch.no_grad():
+        la, lb = a["model"].eval()(probe)["logits"], b["model"].eval()(probe)["logits"]
+    assert rel_err(la, lb) < 2e-2 and torch.equal(la.argmax(1), lb.argmax(1))
+
+
 @pytest.mark.parametrize("amp", [False, True])
 def test_stochastic_depth_matches_oracle_with_shared_masks(amp):
     """drop_path_rate > 0 (the reference's default is 0.4, config.yaml:32): per-sample keep masks,
