@@ -63,7 +63,6 @@ def main() -> None:
             step(x[j:j + batch], y[j:j + batch])
 
         t_graph = timed(graphed)
-        t_eager2 = None
         print(f"{backbone} batch {batch}: eager {t_eager:.3f} ms/step ({batch / t_eager * 1e3:.0f} images/s), "
               f"graph replay {t_graph:.3f} ms/step ({batch / t_graph * 1e3:.0f} images/s)")
         del step, net, opt, arena
