@@ -51,6 +51,20 @@ def test_ops_are_registered_as_torch_library_custom_ops():
         assert callable(getattr(ops, n).fn)
 
 
+def test_weight_gradient_split_k_fills_the_cta_pairs():
+    """Split-K choice for the weight-gradient GEMMs (256 x 256 tiles on 74 CTA pairs): whole waves at the
+    ViT-B / ViT-L shapes, no split for problems with too few k-blocks."""
+    from fedvit_b200.vit import _split_k_for
+
+    tokens = 256 * 197
+    assert [_split_k_for(o, i, tokens) for o, i in ((3072, 768), (768, 3072), (2304, 768), (768, 768))] == [2, 2, 8, 8]
+    for o, i, t in ((4096, 1024, 64 * 577), (3072, 1024, 64 * 577), (3072, 768, tokens)):
+        s = _split_k_for(o, i, t)
+        items = -(-o // 256) * -(-i // 256) * s
+        assert items / (-(-items // 74) * 74) > 0.95
+    assert _split_k_for(512, 768, 256) == 1 and _split_k_for(576, 192, 394) == 1
+
+
 def test_state_dict_keys_and_groups_match_oracle(golden_rgb):
     cfg = micro_config()
     ours = model.build_model(cfg)
