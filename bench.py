@@ -79,6 +79,8 @@ class ClockSampler:
         self._thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self) -> None:
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -88,6 +90,38 @@ class ClockSampler:
             except Exception:
                 pass
             self._stop.wait(0.2)
+
+    def _run_nvml(self) -> bool:
+        """The same readings straight from NVML, every 10 ms (a timed region of ten steps lasts a third of a
+        second; an nvidia-smi process per sample gets one or two readings out of it). Rows keep the
+        nvidia-smi column layout. False = NVML not usable here, fall back to nvidia-smi."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._index)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_fn(h)
+        except Exception:
+            return False
+        bits = (0x8, 0x40, 0x20, 0x4)  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = int(reasons_fn(h))
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                except Exception:
+                    power = 0.0
+                self.rows.append([str(sm), str(mx), f"{power:.1f}"] +
+                                 ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+        return True
 
     def __enter__(self):
         self._thread.start()
