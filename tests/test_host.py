@@ -51,6 +51,20 @@ def test_ops_are_registered_as_torch_library_custom_ops():
         assert callable(getattr(ops, n).fn)
 
 
+def test_bench_clock_summary_parses_sampler_rows():
+    """bench.ClockSampler.summary over rows in the nvidia-smi column layout (what both the NVML and the
+    nvidia-smi samplers append): median clock, max clock, throttle reasons seen in any sample."""
+    import bench
+
+    c = bench.ClockSampler(0)
+    c.rows = [["1700", "1965", "950.2", "Not Active", "Not Active", "Not Active", "Active"],
+              ["1650", "1965", "990.0", "Not Active", "Not Active", "Not Active", "Not Active"],
+              ["1600", "1965", "990.0", "Not Active", "Active", "Not Active", "Not Active"]]
+    got = c.summary()
+    assert got == {"sm_mhz": 1650.0, "sm_max_mhz": 1965.0, "reasons": ["hw_thermal_slowdown", "sw_power_cap"], "samples": 3}
+    assert bench.ClockSampler(0).summary()["samples"] == 0
+
+
 def test_weight_gradient_split_k_fills_the_cta_pairs():
     """Split-K choice for the weight-gradient GEMMs (256 x 256 tiles on 74 CTA pairs): whole waves at the
     ViT-B / ViT-L shapes, no split for problems with too few k-blocks."""
