@@ -9,7 +9,12 @@ round it feeds (BASELINE.json metric, configs[1]).
 A "step" is one client optimisation step on one batch of 256 synthetic 224x224x3 images:
 forward, asymmetric-focal loss, backward, global-norm clip + AdamW (LLRD groups) — everything the
 reference does per iteration of train.py:131-166. Prints ONE JSON line (rank 0).
-  value     images/s over all GPUs, batches resident in HBM when the timed region starts
+  value     images/s over all GPUs, batches resident in HBM when the timed region starts (no
+            instrumentation inside the region)
+  fedavg    3 REAL rounds through train.run_federated (first = warm-up): round_ms, aggregate_ms, the gap to
+            16 x ms_per_step; parity_rel = NCCL aggregate vs the sequential fixed-order sum (gate 1e-6)
+  extra_configs  short runs of BASELINE configs 3 / 4 / 5 (masked ViT-B, ViT-L/16 384 step and non-IID
+            round with unequal shards, eval sweep)
   e2e       the same through the public API (train.train_one_epoch) from pinned HOST batches:
             per-step host->device copies and a device->host read of the loss are inside the timing
   roofline  tensor-core GEMM kernel: algorithmic FLOPs / CUDA-event time of its launches, live in
@@ -235,33 +240,6 @@ def run_gpu_arm(args) -> None:
     else:
         saved_stdout = None
 
-    cfg = model_config()
-    cfg["model"]["cls_only_last_block"] = bool(args.cls_only_last_block)
-    utils.seed_everything(42)
-    net = model.build_model(cfg).to(dev).train()
-    arena = FlatArena(net)
-    fedavg.broadcast_initial(arena, net)
-    opt = optim.FusedAdamW(model.get_layerwise_lr_groups(net, 1e-4, 0.75, 1e-5), weight_decay=1e-5, arena=arena)
-    crit = losses.build_loss(cfg)
-    agg = fedavg.FedAvgAggregator(net, arena)
-
-    pool = 4
-    g = torch.Generator().manual_seed(1000 + rank)  # client id == rank
-    host_x = torch.randn(pool * BATCH, 3, IMG, IMG, generator=g).pin_memory()
-    host_y = torch.randint(0, CLASSES, (pool * BATCH,), generator=g).pin_memory()
-    dev_x, dev_y = host_x.to(dev), host_y.to(dev)
-
-    def step(i: int):
-        j = (i % pool) * BATCH
-        x, y = dev_x[j:j + BATCH], dev_y[j:j + BATCH]
-        opt.zero_grad(set_to_none=True)
-        with torch.amp.autocast("cuda", dtype=torch.bfloat16):
-            loss = crit(net(x)["logits"], y)
-        loss.backward()
-        utils.clip_grad_norm(net.parameters(), 1.0, optimizer=opt)
-        opt.step()
-        return loss
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -274,43 +252,84 @@ def run_gpu_arm(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    # ---- device-resident throughput ---------------------------------------------------------------
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    ops.GEMM_TRACE = None if os.environ.get("FEDVIT_BENCH_NOTRACE") else []  # A/B switch: cost of the per-GEMM events
-    n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    def make_stepper(cfg, batch, img, chans, seed_rank=True):
+        """Model + arena + fused optimiser + a pool of 4 distinct device-resident batches (larger than L2
+        together with the ~17 GB of activations a step writes) and the closure that runs one client step."""
+        utils.seed_everything(42)
+        net = model.build_model(cfg).to(dev).train()
+        arena = FlatArena(net)
+        fedavg.broadcast_initial(arena, net)
+        opt = optim.FusedAdamW(model.get_layerwise_lr_groups(net, 1e-4, 0.75, 1e-5), weight_decay=1e-5, arena=arena)
+        crit = losses.build_loss(cfg)
+        pool = 4
+        g = torch.Generator().manual_seed(1000 + (rank if seed_rank else 0))  # client id == rank
+        host_x = torch.randn(pool * batch, chans, img, img, generator=g)
+        if chans == 4:  # lesion-mask plane in {-1, +1} (data.py:153-154)
+            host_x[:, 3] = (torch.bernoulli(torch.full((pool * batch, img, img), 0.3), generator=g) - 0.5) / 0.5
+        host_x = host_x.pin_memory()
+        host_y = torch.randint(0, CLASSES, (pool * batch,), generator=g).pin_memory()
+        dev_x, dev_y = host_x.to(dev), host_y.to(dev)
+
+        def step(i: int):
+            j = (i % pool) * batch
+            x, y = dev_x[j:j + batch], dev_y[j:j + batch]
+            opt.zero_grad(set_to_none=True)
+            with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+                loss = crit(net(x)["logits"], y)
+            loss.backward()
+            utils.clip_grad_norm(net.parameters(), 1.0, optimizer=opt)
+            opt.step()
+            return loss
+
+        return net, arena, opt, crit, step, host_x, host_y, pool
+
+    def time_steps(step, warmup, steps, sample_clocks=False):
+        for i in range(warmup):
+            step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler is not None:
+            sampler.__enter__()
         barrier()
         e0.record()
-        for i in range(args.steps):
-            loss = step(args.warmup + i)
+        for i in range(steps):
+            loss = step(warmup + i)
         e1.record()
         barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+        if sampler is not None:
+            sampler.__exit__()
+        return max_over_ranks(e0.elapsed_time(e1)), loss, sampler
+
+    cfg = model_config()
+    cfg["model"]["cls_only_last_block"] = bool(args.cls_only_last_block)
+    net, arena, opt, crit, step, host_x, host_y, pool = make_stepper(cfg, BATCH, IMG, 3)
+
+    # ---- headline: device-resident throughput, nothing but the steps inside the timed region --------
+    ops.GEMM_TRACE = None
+    n0 = _lib.launch_count()
+    ms_total, loss, clocks = time_steps(step, args.warmup, args.steps, sample_clocks=True)
     launches = _lib.launch_count() - n0
-    trace, ops.GEMM_TRACE = ops.GEMM_TRACE or [], None
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in trace)
-    gemm_flops = sum(f for _, _, f in trace)
+    state_bytes = arena.numel * 4
     final_loss = float(loss.detach())
     ms_step = ms_total / args.steps
     value = args.gpus * BATCH * args.steps / (ms_total / 1e3)
 
-    # ---- FedAvg aggregate (fold + allreduce + install), timed on the device ---------------------------
-    agg.begin_round()
-    agg_ms = []
-    for _ in range(3):
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        agg._folded = 0
-        agg.fold(STEPS_PER_ROUND * BATCH, STEPS_PER_ROUND * BATCH * args.gpus, client_id=rank)
-        agg.finish()
-        a1.record()
-        barrier()
-        agg_ms.append(max_over_ranks(a0.elapsed_time(a1)))
-    aggregate_ms = min(agg_ms)
+    # ---- roofline leg: a SECOND pass with every tensor-core GEMM launch bracketed by CUDA events -------
+    # (2 960 event pairs per 10 steps: kept out of the headline region — r1 timed both at once)
+    trace_steps = max(2, min(5, args.steps))
+    ops.GEMM_TRACE = []
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(trace_steps):
+        step(args.warmup + args.steps + i)
+    t1.record()
+    barrier()
+    trace_ms_total = t0.elapsed_time(t1)
+    trace, ops.GEMM_TRACE = ops.GEMM_TRACE or [], None
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in trace)
+    gemm_flops = sum(f for _, _, f in trace)
 
     # ---- end to end through the public API: pinned host batches, H2D per step, loss read per step ----
     class HostLoader:
@@ -337,16 +356,196 @@ def run_gpu_arm(args) -> None:
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = args.gpus * BATCH * args.steps / (e2e_ms / 1e3)
 
+    # ---- FedAvg aggregate alone (last fold in place + allreduce + bf16 re-cast), timed on the device ----
+    agg = fedavg.FedAvgAggregator(net, arena)
+    n_k = STEPS_PER_ROUND * BATCH
+    agg_ms = []
+    for _ in range(3):
+        agg.begin_round(1)
+        agg.load_global()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        agg.fold(n_k, n_k * args.gpus, client_id=rank, last=True)
+        agg.finish()
+        a1.record()
+        barrier()
+        agg_ms.append(max_over_ranks(a0.elapsed_time(a1)))
+    aggregate_ms = min(agg_ms)
+
+    # ---- NCCL aggregate vs the sequential fixed-order sum (north_star: 1e-6 relative) --------------------
+    # every rank contributes a different pseudo-client (its trained weights + a rank-seeded perturbation)
+    # with unequal n_k; the product path (pre-scaled fold + ncclAllReduce) against acc = fl(c_0 w_0),
+    # acc = fl(acc + fl(c_k w_k)) in rank order on one GPU — the oracle's order of operations
+    parity_rel = None
+    sizes_p = [n_k + 256 * r for r in range(args.gpus)]
+    with torch.no_grad():
+        base = arena.params.clone()
+        gp = torch.Generator(device=dev).manual_seed(77 + rank)
+        arena.params.add_(torch.randn(arena.numel, device=dev, generator=gp) * 1e-2 * base.abs().mean())
+        mine_w = arena.params.clone()
+        agg.begin_round(1)
+        agg.load_global()
+        agg.fold(sizes_p[rank], sum(sizes_p), client_id=rank, last=True)
+        agg.finish()
+        if world > 1:
+            gathered = [torch.empty_like(mine_w) for _ in range(world)]
+            dist.all_gather(gathered, mine_w)
+            seq = None
+            for r in range(world):
+                term = gathered[r] * torch.tensor(fedavg.client_weight(sizes_p[r], sum(sizes_p)), device=dev)
+                seq = term if seq is None else seq + term
+            parity_rel = float((arena.params.double() - seq.double()).norm() / seq.double().norm())
+            del gathered, seq
+        else:
+            seq = mine_w * torch.tensor(fedavg.client_weight(sizes_p[0], sum(sizes_p)), device=dev)
+            parity_rel = float((arena.params.double() - seq.double()).norm() / seq.double().norm())
+        arena.params.copy_(base)
+        arena.refresh_lp(force=True)
+        del base, mine_w
+
     if world > 1:
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt)
 
+    # free the headline model before the round / extra-config legs build their own
+    del net, arena, opt, crit, step, agg, host_x, host_y
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    quiet = type("Q", (), {"info": staticmethod(lambda *a, **k: None)})()
+
+    # ---- the metric's second half: REAL FedAvg rounds through train.run_federated ------------------------
+    # configs[1]: one client per GPU, n_k = 4096 (16 steps of 256), 1 local epoch; 3 rounds, first = warm-up;
+    # CUDA events around the whole round incl. its opening barrier (run_federated's own timing, max over ranks)
+    fed_cfg = model_config()
+    fed_cfg["federated"] = {"num_clients": args.gpus, "rounds": 3, "local_epochs": 1, "samples_per_client": n_k,
+                            "partition": "iid", "synthetic_pool": 4 * BATCH}
+    fed_out = train.run_federated(fed_cfg, device=dev, logger=quiet, device_resident=True)
+    rounds = fed_out["rounds"]
+    timed = rounds[1:]
+    round_ms = min(r["round_ms"] for r in timed)
+    round_info = {
+        "round_ms": round_ms, "round_ms_all": [r["round_ms"] for r in rounds], "warmup_rounds": 1,
+        "aggregate_ms_in_round": min(r["aggregate_ms"] for r in timed),
+        "round_images_per_s": args.gpus * n_k / (round_ms / 1e3),
+        "steps_x_ms_step": STEPS_PER_ROUND * ms_step,
+        "gap_to_steps_ms": round_ms - STEPS_PER_ROUND * ms_step,
+        "api": "fedvit_b200.train.run_federated, device-resident client shards (pool of 4 batches cycled), "
+               "load_global + optimiser reset + 16 x train_one_epoch steps + in-place fold + allreduce + install",
+    }
+    del fed_out
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---- configs 3 / 4 / 5: short driver-visible runs (not the headline; each a few seconds) --------------
+    extra = {}
+    if not args.no_extra:
+        peaks_x = measured_peaks()
+        peak_x = peaks_x["bf16_tflops_sustained"] or peaks_x["bf16_tflops"]
+        # config 4 as a ROUND at every N: ViT-L/16 384, 2 clients per GPU, unequal non-IID shards
+        k4 = 2 * args.gpus
+        sizes4 = [64 * (2 + (5 * c) % 7) for c in range(k4)]  # 128 ... 512 samples, batch 64: 2 ... 8 steps
+        cfg4 = model_config()
+        cfg4["model"].update({"backbone": "vit_large_patch16_384", "image_size": 384})
+        cfg4["training"]["batch_size"] = 64
+        cfg4["federated"] = {"num_clients": k4, "rounds": 2, "local_epochs": 1, "samples_per_client": sizes4,
+                             "partition": "dirichlet", "dirichlet_alpha": 0.5, "synthetic_pool": 128}
+        out4 = train.run_federated(cfg4, device=dev, logger=quiet, device_resident=True)
+        r4 = out4["rounds"][-1]
+        place = out4["placement"]
+        loads = [sum(sizes4[c] for c in cs) for cs in place]
+        busy = r4["rank_busy_ms"]
+        rate = sum(loads) / (sum(busy) / 1e3)  # images per GPU-second actually achieved while busy
+        extra["config4_round_vit_large_384"] = {
+            "workload": f"ViT-Large/16 384px bf16, {k4} non-IID (Dirichlet 0.5) clients over {args.gpus} GPU(s), "
+                        "unequal n_k, sample-weighted FedAvg; round 2 of 2 (shards scaled down 4x from 512...2048)",
+            "samples_per_client": sizes4, "placement": place, "samples_per_rank": loads,
+            "round_ms": r4["round_ms"], "aggregate_ms": r4["aggregate_ms"], "rank_busy_ms": busy,
+            "images_per_s": r4["images_per_s"],
+            "imbalance_max_over_mean_busy": max(busy) / (sum(busy) / len(busy)),
+            "round_ms_over_balanced_ideal": r4["round_ms"] / (sum(loads) / args.gpus / rate * 1e3),
+            "state_bytes": out4["arena"].numel * 4,
+        }
+        del out4
+        gc.collect()
+        torch.cuda.empty_cache()
+        if world == 1:
+            # config 3: masked path (4-channel patch GEMM, K = 1024)
+            cfg3 = model_config()
+            cfg3["data"]["use_segmentation_mask"] = True
+            s3 = make_stepper(cfg3, BATCH, IMG, 4)
+            ms3, _, _ = time_steps(s3[4], 3, 5)
+            v3 = BATCH * 5 / (ms3 / 1e3)
+            extra["config3_vit_base_masked"] = {
+                "workload": "ViT-Base/16 224px, 4-channel input (RGB + lesion mask), bf16, batch 256, 5 timed steps",
+                "images_per_s": v3, "ms_per_step": ms3 / 5, "train_gflop_per_img": 105.612,
+                "step_frac_of_peak": v3 * 105.612 / 1e3 / peak_x}
+            del s3
+            gc.collect()
+            torch.cuda.empty_cache()
+            # config 4: ViT-L/16 384, batch 64, one GPU's step
+            cfg4s = model_config()
+            cfg4s["model"].update({"backbone": "vit_large_patch16_384", "image_size": 384})
+            s4 = make_stepper(cfg4s, 64, 384, 3)
+            ms4, _, _ = time_steps(s4[4], 3, 3)
+            v4 = 64 * 3 / (ms4 / 1e3)
+            extra["config4_vit_large_384_step"] = {
+                "workload": "ViT-Large/16 384px bf16, batch 64, 3 timed client steps on one GPU",
+                "images_per_s": v4, "ms_per_step": ms4 / 3, "train_gflop_per_img": 1146.395,
+                "step_frac_of_peak": v4 * 1146.395 / 1e3 / peak_x}
+            del s4
+            gc.collect()
+            torch.cuda.empty_cache()
+            # config 5: forward-only eval sweep (eager; CUDA-graph replay where the forward is launch-bound)
+            from fedvit_b200.graphs import GraphedForward
+
+            utils.seed_everything(42)
+            enet = model.build_model(model_config()).to(dev).eval()
+            FlatArena(enet)
+            sweep = []
+            for b in (1, 32, 256, 1024):
+                xb = torch.randn(b, 3, IMG, IMG, device=dev)
+                row = {"batch": b}
+                for mode in (("eager", "graph") if b <= 32 else ("eager",)):
+                    if mode == "graph":
+                        fwd = GraphedForward(enet, xb)
+                        run = lambda: fwd(xb)
+                    else:
+                        def run():
+                            with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
+                                return enet(xb)["logits"]
+                    for _ in range(5):
+                        run()
+                    torch.cuda.synchronize(dev)
+                    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    iters = 20
+                    q0.record()
+                    for _ in range(iters):
+                        run()
+                    q1.record()
+                    torch.cuda.synchronize(dev)
+                    ms = q0.elapsed_time(q1) / iters
+                    row[f"{mode}_ms"] = ms
+                    row[f"{mode}_images_per_s"] = b / (ms / 1e3)
+                best = max(v for k, v in row.items() if k.endswith("images_per_s"))
+                row["fwd_frac_of_peak"] = best * 35.127 / 1e3 / peak_x
+                sweep.append(row)
+            extra["config5_eval_sweep_vit_base"] = {
+                "workload": "ViT-Base/16 forward-only (validate's per-batch work), bf16, 20 timed iterations after 5 warm-up",
+                "fwd_gflop_per_img": 35.127, "rows": sweep}
+            del enet
+            gc.collect()
+            torch.cuda.empty_cache()
+
     if rank == 0:
         peaks = measured_peaks()
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        tpath = ROOT / "profiles" / "r1_ncu_traffic.json"
-        traffic = json.loads(tpath.read_text()) if tpath.exists() else {}
+        tpath = next((q for q in (ROOT / "profiles" / "r2_ncu_traffic.json", ROOT / "profiles" / "r1_ncu_traffic.json")
+                      if q.exists()), None)
+        traffic = json.loads(tpath.read_text()) if tpath else {}
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -366,18 +565,23 @@ def run_gpu_arm(args) -> None:
                 "bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM: CTA-pair and single-CTA variants, all epilogues)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                "gemm_launches": len(trace), "gemm_share_of_step": gemm_ms / ms_total if ms_total else None,
+                "measured_in": f"a separate pass of {trace_steps} steps with per-launch CUDA events (the headline region "
+                               "carries no instrumentation)",
+                "gemm_launches": len(trace), "gemm_share_of_step": gemm_ms / trace_ms_total if trace_ms_total else None,
                 "traffic": traffic.get("dram_bytes_per_launch"), "traffic_unit": "bytes per launch",
                 "traffic_note": (f"ncu --set full, one launch of {traffic.get('kernel')} at {traffic.get('shape')}: "
                                  f"{traffic.get('dram_bytes_per_launch')} B DRAM vs {traffic.get('algorithmic_bytes_per_launch')} B "
                                  f"algorithmic, tensor pipe active {traffic.get('tensor_pipe_active_pct_of_elapsed')} % of elapsed "
-                                 f"({traffic.get('source')})") if traffic else None,
+                                 f"({traffic.get('source')}; captured at {traffic.get('commit', 'round 1')})") if traffic else None,
                 "step_tflops": value / args.gpus * TRAIN_GFLOP_PER_IMG / 1e3,
                 "step_frac_of_peak": value / args.gpus * TRAIN_GFLOP_PER_IMG / 1e3 / peak,
             },
-            "fedavg": {"aggregate_ms": aggregate_ms, "steps_per_round": STEPS_PER_ROUND,
-                       "round_ms": STEPS_PER_ROUND * ms_step + aggregate_ms,
-                       "state_bytes": arena.numel * 4},
+            "fedavg": dict(round_info, aggregate_ms=aggregate_ms, steps_per_round=STEPS_PER_ROUND,
+                           state_bytes=state_bytes,
+                           parity_rel=parity_rel, parity_gate=1e-6,
+                           parity_note="NCCL allreduce of pre-scaled client weights vs the sequential fixed-order "
+                                       "fp32 sum in rank order (all-gathered, summed on one GPU)"),
+            "extra_configs": extra,
             "loss": final_loss,
         }
         if args.gpus == 1 and not args.no_cpu_baseline:
@@ -404,6 +608,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="fedvit", choices=["fedvit", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs legs (configs 3 / 4 / 5)")
     ap.add_argument("--cls-only-last-block", action="store_true",
                     help="opt-in model.cls_only_last_block: the last block's token-wise tail on the cls rows only "
                          "(same logits / gradients, ~4 %% fewer FLOPs); NOT the default measurement")

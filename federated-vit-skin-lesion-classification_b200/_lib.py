@@ -113,3 +113,14 @@ LIB = _Lib()
 
 def launch_count() -> int:
     return int(LIB.raw("fv_launch_count")())
+
+
+# kernel families of fv_kernel_launches (include/fedvit.h: FV_KERNEL_*)
+KERNEL_GEMM_TC, KERNEL_GEMM_TC_PAIR, KERNEL_ATTN_FWD, KERNEL_ATTN_BWD = 0, 1, 2, 3
+KERNEL_ATTN_FWD_LONG, KERNEL_ATTN_BWD_LONG, KERNEL_ATTN_LEGACY = 4, 5, 6
+
+
+def kernel_launches(family: int) -> int:
+    """How many kernels of one family the library has launched since load: lets a test assert which
+    kernel served a call (e.g. that a ViT-B step ran on the CTA-pair GEMM)."""
+    return int(LIB.raw("fv_kernel_launches")(family))

@@ -49,6 +49,9 @@ class FlatArena:
         self.grads = torch.zeros(off, device=dev, dtype=torch.float32)
         self.lp = torch.zeros(off, device=dev, dtype=torch.bfloat16) if with_lp else None
         self._lp_versions: Optional[List[int]] = None
+        # True while the gradient buffer is known to hold zeros (fresh, zeroed, or just swept by an
+        # optimiser step that wrote zeros back): zero_grads() is then free. Every backward clears it.
+        self.grads_clean = True
         # per-parameter views of the gradient buffer and the bf16 shadow, made once: every step asks for
         # each of them several times (zero_grad, clip, the optimiser's foreign-gradient check, the GEMMs'
         # weight operands), and slicing + reshaping ~150 tensors costs the host about a millisecond a time
@@ -85,7 +88,9 @@ class FlatArena:
                 p.grad = self._cached(self._grad_views, self.grads, n)
 
     def zero_grads(self) -> None:
-        self.grads.zero_()
+        if not self.grads_clean:
+            self.grads.zero_()
+            self.grads_clean = True
         self.attach_grads()
 
     def owns(self, p: nn.Parameter) -> bool:

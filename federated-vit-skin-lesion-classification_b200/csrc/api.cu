@@ -20,6 +20,11 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<int64_t> g_family[FV_KERNEL_FAMILIES];
+void count_kernel(int family) {
+  if (family >= 0 && family < FV_KERNEL_FAMILIES) g_family[family].fetch_add(1, std::memory_order_relaxed);
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -62,3 +67,7 @@ EncodeTiledFn get_encode_tiled() {
 extern "C" int fv_version(void) { return 100; }
 extern "C" const char* fv_last_error(void) { return fv::g_error; }
 extern "C" int64_t fv_launch_count(void) { return fv::g_launches.load(std::memory_order_relaxed); }
+extern "C" int64_t fv_kernel_launches(int family) {
+  if (family < 0 || family >= FV_KERNEL_FAMILIES) return -1;
+  return fv::g_family[family].load(std::memory_order_relaxed);
+}

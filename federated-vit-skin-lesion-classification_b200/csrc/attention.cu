@@ -534,6 +534,7 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
   FV_CHECK_CUDA(fv::launch_pdl(attn_fwd_kernel, dim3(grid), dim3(AT_THREADS), 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse,
       (int)tokens, (int)heads, scale));
+  count_kernel(FV_KERNEL_ATTN_LEGACY);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

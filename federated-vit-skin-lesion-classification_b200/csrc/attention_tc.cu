@@ -285,6 +285,7 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
   const int slots = 2 * num_sms();  // two co-resident CTAs per SM
   const unsigned grid = static_cast<unsigned>(p.items < slots ? p.items : slots);
   FV_CHECK_CUDA(fv::launch_pdl(attn_tc_fwd_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, mq, mkv, p));
+  count_kernel(FV_KERNEL_ATTN_FWD);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -804,6 +805,7 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
   }
   const int grid = p.items < num_sms() ? p.items : num_sms();
   FV_CHECK_CUDA(fv::launch_pdl(attn_tc_bwd_kernel, dim3(static_cast<unsigned>(grid)), dim3(ATB_THREADS), ATB_SMEM, stream, mq, mdo, mdq, p));
+  count_kernel(FV_KERNEL_ATTN_BWD);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -1100,6 +1102,7 @@ int attention_tc_fwd_long(const void* qkv, void* out, float* lse, int64_t batch,
   const int grid = p.items < num_sms() ? p.items : num_sms();
   FV_CHECK_CUDA(fv::launch_pdl(attn_tc_fwd_long_kernel, dim3(static_cast<unsigned>(grid)), dim3(ATL_THREADS), smem, stream,
                                map, p));
+  count_kernel(FV_KERNEL_ATTN_FWD_LONG);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -1552,6 +1555,7 @@ int attention_tc_bwd_long(const void* qkv, const void* dout, const float* lse, c
   const int grid = p.items < num_sms() ? p.items : num_sms();
   FV_CHECK_CUDA(fv::launch_pdl(attn_tc_bwd_long_kernel, dim3(static_cast<unsigned>(grid)), dim3(ATLB_THREADS), smem, stream,
                                mq, mdo, mdq, p));
+  count_kernel(FV_KERNEL_ATTN_BWD_LONG);
   FV_LAUNCH_CHECK();
   const long long rows = batch * tokens;
   const long long total = rows * (hd / 8);

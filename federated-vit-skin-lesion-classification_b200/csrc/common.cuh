@@ -15,6 +15,7 @@ namespace fv {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void count_kernel(int family);  // per-kernel-family launch counters (FV_KERNEL_*, fv_kernel_launches)
 int num_sms();
 
 #define FV_CHECK_ARG(cond, ...)                    \

@@ -52,6 +52,43 @@ cls_pos_kernel(const float* __restrict__ cls, const float* __restrict__ pos, flo
   }
 }
 
+// Head of the backward: the loss reaches the backbone through the cls token only (model.py:193 pools
+// timm's global_pool='token'), so the gradient entering the last block is dcls in row 0 of every image
+// and zero elsewhere. One pass writes both forms the last block's backward reads — the fp32 residual-
+// path gradient and its bf16 copy times the block's stochastic-depth factor — instead of
+// zeros + slice-assign + clone + cast (four passes over [B*N, D]).
+__global__ void __launch_bounds__(256)
+cls_grad_rows_kernel(const float* __restrict__ dcls, const float* __restrict__ row_scale, float* __restrict__ dx,
+                     void* __restrict__ dy, int dy_bf16, int batch, int tokens, int dim) {
+  pdl_wait();
+  const int dq = dim >> 2;
+  const long long total = static_cast<long long>(batch) * tokens * dq;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % dq);
+    const long long row = i / dq;
+    const int tok = static_cast<int>(row % tokens);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), s = v;
+    if (tok == 0) {
+      const int b = static_cast<int>(row / tokens);
+      v = reinterpret_cast<const float4*>(dcls)[static_cast<long long>(b) * dq + c];
+      const float f = row_scale != nullptr ? row_scale[b] : 1.0f;
+      s = make_float4(v.x * f, v.y * f, v.z * f, v.w * f);
+    }
+    if (dx != nullptr) __stcs(reinterpret_cast<float4*>(dx) + i, v);
+    if (dy != nullptr) {
+      if (dy_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16(s.x, s.y);
+        pk.y = pack_bf16(s.z, s.w);
+        reinterpret_cast<uint2*>(dy)[i] = pk;
+      } else {
+        reinterpret_cast<float4*>(dy)[i] = s;
+      }
+    }
+  }
+}
+
 // out[c] += sum_r a[r, c].  block = 32 x 8; a warp row covers 64 columns (2 per lane).
 // VEC2 = false: scalar loads for odd widths / leading dimensions (the 7-class head's bias gradient).
 template <bool IN_BF16, bool VEC2 = true>
@@ -224,6 +261,23 @@ extern "C" int fv_softmax_rows_bwd(const float* p, const float* dp, float* ds, i
   if (rows == 0) return FV_OK;
   FV_CHECK_CUDA(fv::launch_pdl(softmax_rows_bwd_kernel, dim3(static_cast<unsigned>(ceil_div(rows, 8))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       p, dp, ds, rows, (int)cols, scale));
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_cls_grad_rows(const float* dcls, const float* row_scale, float* dx, void* dy, int dy_dtype,
+                                int64_t batch, int64_t tokens, int64_t dim, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(dcls && (dx || dy) && batch > 0 && tokens > 0 && dim > 0 && dim % 4 == 0,
+               "fv_cls_grad_rows: bad argument");
+  FV_CHECK_ARG(dy_dtype == FV_F32 || dy_dtype == FV_BF16, "fv_cls_grad_rows: dy_dtype");
+  const long long total = batch * tokens * (dim >> 2);
+  long long blocks = ceil_div(total, 256 * 4);
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  FV_CHECK_CUDA(fv::launch_pdl(cls_grad_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+                               static_cast<cudaStream_t>(stream), dcls, row_scale, dx, dy,
+                               dy_dtype == FV_BF16 ? 1 : 0, (int)batch, (int)tokens, (int)dim));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

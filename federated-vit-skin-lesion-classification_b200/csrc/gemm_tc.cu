@@ -1205,6 +1205,7 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     if (v > 0 && v < grid) grid = v;
   }
   FV_CHECK_CUDA(fv::launch_pdl(gemm_tc_kernel<EPI, BF16>, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, stream, ta, tb, tc, tx, p));
+  count_kernel(FV_KERNEL_GEMM_TC);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }
@@ -1223,6 +1224,7 @@ static int launch_gemm_tc2(const CUtensorMap& ta, const CUtensorMap& tb, const C
   if (clusters > total) clusters = total;
   FV_CHECK_CUDA(fv::launch_pdl_cluster(gemm_tc2_kernel<EPI, BF16>, dim3(2 * clusters), dim3(GEMM_THREADS),
                                        GEMM_SMEM_BYTES, stream, 2u, ta, tb, tc, tx, p));
+  count_kernel(FV_KERNEL_GEMM_TC_PAIR);
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

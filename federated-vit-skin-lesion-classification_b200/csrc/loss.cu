@@ -27,9 +27,15 @@ loss_kernel(const float* __restrict__ logits, const long long* __restrict__ targ
   const bool live = lane < classes;
   const float inv_b = 1.0f / batch;
   float acc = 0.f;
+  bool bad = false;
   for (int row = warp; row < batch; row += LOSS_WARPS) {
     const float z = live ? logits[row * classes + lane] : -INFINITY;
-    const int t = static_cast<int>(targets[row]);
+    const long long t64 = targets[row];
+    // a label outside [0, classes) makes F.one_hot / nll_loss raise in the reference; a kernel cannot
+    // raise, so the loss (and with it every gradient downstream) becomes NaN instead of silently
+    // training on a row without a positive class
+    if (t64 < 0 || t64 >= classes) bad = true;
+    const int t = static_cast<int>(t64);
     const float zmax = warp_max(z);
     const float e = live ? expf(z - zmax) : 0.f;
     const float denom = warp_sum(e);
@@ -45,7 +51,12 @@ loss_kernel(const float* __restrict__ logits, const long long* __restrict__ targ
           const float w = powf(om, gamma_pos);
           const float lg = logf(pp);
           term = -w * lg;
-          const float dw = (1.0f - p >= 0.f) ? -gamma_pos * powf(om, gamma_pos - 1.0f) : 0.f;
+          // d/dp (1-p)^g: torch's pow backward returns 0 for exponent 0 (and never forms 0 * inf): with
+          // gamma_pos = 0 (the ASL paper's default) and a saturated softmax, powf(0, -1) = inf would
+          // turn the product into NaN
+          const float dw = (gamma_pos == 0.f || !(1.0f - p >= 0.f)) ? 0.f
+                           : (om == 0.f && gamma_pos < 1.0f) ? 0.f
+                           : -gamma_pos * powf(om, gamma_pos - 1.0f);
           const float dlg = (p >= eps) ? 1.0f / pp : 0.f;
           dl_dp = -(dw * lg + w * dlg);
         } else {
@@ -62,7 +73,9 @@ loss_kernel(const float* __restrict__ logits, const long long* __restrict__ targ
           const float w = powf(pc, gamma_neg);
           const float lg = logf(1.0f - pn);
           term = -w * lg;
-          const float dw = (p >= 0.f) ? gamma_neg * powf(pc, gamma_neg - 1.0f) : 0.f;
+          const float dw = (gamma_neg == 0.f || !(p >= 0.f)) ? 0.f
+                           : (pc == 0.f && gamma_neg < 1.0f) ? 0.f
+                           : gamma_neg * powf(pc, gamma_neg - 1.0f);
           const float dlg = -dpn / (1.0f - pn);
           dl_dp = -(dw * lg + w * dlg);
         }
@@ -82,7 +95,7 @@ loss_kernel(const float* __restrict__ logits, const long long* __restrict__ targ
         dlogits[row * classes + lane] = (p - (lane == t ? 1.0f : 0.f)) * inv_b;
     }
   }
-  if (lane == 0) warp_loss[warp] = acc;
+  if (lane == 0) warp_loss[warp] = bad ? __int_as_float(0x7fc00000) : acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float s = 0.f;

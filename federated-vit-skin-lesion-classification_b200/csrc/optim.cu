@@ -59,12 +59,13 @@ __device__ __forceinline__ float clip_coef(const float* sumsq, float max_norm) {
 
 template <bool HAS_EMA, bool HAS_LP>
 __global__ void __launch_bounds__(SWEEP_THREADS)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, const long long* __restrict__ seg_end,
              const float* __restrict__ seg_lr, const float* __restrict__ seg_wd, int nseg,
              const float* __restrict__ sumsq, float max_norm, float beta1, float beta2, float eps,
              float bc1, float bc2_sqrt, float* __restrict__ ema, float ema_decay,
-             __nv_bfloat16* __restrict__ p_lp, long long nvec, const float* __restrict__ bc_dev) {
+             __nv_bfloat16* __restrict__ p_lp, long long nvec, const float* __restrict__ bc_dev,
+             int zero_grad) {
   pdl_wait();
   if (bc_dev != nullptr) {  // captured in a CUDA graph: the step-dependent bias corrections live in device memory
     bc1 = __ldg(bc_dev);
@@ -92,8 +93,13 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     }
     const float lr = s_lr[lo], wd = s_wd[lo];
     float4 pv = reinterpret_cast<float4*>(p)[i];
+    // zero_grad: this sweep is the gradient's last reader, so it leaves the buffer zeroed for the next
+    // step's accumulating kernels (optimizer.zero_grad, reference train.py:160) — the separate memset
+    // pass over the 345 MB gradient arena disappears. Un-optimised ranges (lr < 0) are zeroed too.
+    if (zero_grad && lr < 0.f) __stcs(reinterpret_cast<float4*>(g) + i, make_float4(0.f, 0.f, 0.f, 0.f));
     if (lr >= 0.f) {
       const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+      if (zero_grad) __stcs(reinterpret_cast<float4*>(g) + i, make_float4(0.f, 0.f, 0.f, 0.f));
       float4 mv = reinterpret_cast<float4*>(m)[i];
       float4 vv = reinterpret_cast<float4*>(v)[i];
       const float decay = 1.0f - lr * wd;
@@ -189,6 +195,38 @@ fedavg_kernel(float* __restrict__ acc, const float* __restrict__ w, float weight
   }
 }
 
+// out = (acc ? acc : 0) + weight * w with the oracle's rounding (one rounded multiply, one rounded add);
+// out may alias w or acc. The LAST fold of a round writes straight into the parameter arena — the buffer
+// the allreduce then runs on in place — instead of into the accumulator followed by a 345 MB copy, and
+// (single rank) emits the bf16 shadow of the new global weights in the same pass.
+template <bool HAS_ACC, bool HAS_LP>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+fedavg_into_kernel(const float* acc, const float* w, float weight, float* out, __nv_bfloat16* out_lp, long long nvec) {
+  pdl_wait();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += stride) {
+    const float4 wv = reinterpret_cast<const float4*>(w)[i];
+    float4 a;
+    if (HAS_ACC) {
+      a = __ldcs(reinterpret_cast<const float4*>(acc) + i);
+      a.x = __fadd_rn(a.x, __fmul_rn(weight, wv.x));
+      a.y = __fadd_rn(a.y, __fmul_rn(weight, wv.y));
+      a.z = __fadd_rn(a.z, __fmul_rn(weight, wv.z));
+      a.w = __fadd_rn(a.w, __fmul_rn(weight, wv.w));
+    } else {
+      a = make_float4(weight * wv.x, weight * wv.y, weight * wv.z, weight * wv.w);
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+    if (HAS_LP) {
+      uint2 pk;
+      pk.x = pack_bf16(a.x, a.y);
+      pk.y = pack_bf16(a.z, a.w);
+      reinterpret_cast<uint2*>(out_lp)[i] = pk;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SWEEP_THREADS)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long nvec) {
   pdl_wait();
@@ -220,11 +258,11 @@ extern "C" int fv_sumsq(const float* g, int64_t n, float* sumsq, int accumulate,
 }
 
 namespace fv {
-static int adamw_flat_impl(float* p, const float* g, float* m, float* v, const int64_t* seg_end,
+static int adamw_flat_impl(float* p, float* g, float* m, float* v, const int64_t* seg_end,
                            const float* seg_lr, const float* seg_wd, int nseg, const float* sumsq,
                            float max_norm, float beta1, float beta2, float eps, int64_t step,
                            const float* bias_corr, float* ema, float ema_decay, void* p_lp, int64_t n,
-                           void* stream) {
+                           int zero_grad, void* stream) {
   FV_CHECK_ARG(p && g && m && v && seg_end && seg_lr && seg_wd, "fv_adamw_flat: null pointer");
   FV_CHECK_ARG(nseg > 0 && nseg <= MAX_SEGMENTS, "fv_adamw_flat: nseg=%d out of range", nseg);
   FV_CHECK_ARG(n > 0 && n % 4 == 0, "fv_adamw_flat: n=%lld must be a positive multiple of 4", (long long)n);
@@ -247,7 +285,7 @@ static int adamw_flat_impl(float* p, const float* g, float* m, float* v, const i
 #define FV_ADAM_LAUNCH(E, L)                                                                      \
   FV_CHECK_CUDA(fv::launch_pdl(adamw_kernel<E, L>, dim3(grid), dim3(SWEEP_THREADS), 0, st, p, g, m, v, se, seg_lr, seg_wd, nseg, sumsq, \
                                                      max_norm, beta1, beta2, eps, fbc1, fbc2s,   \
-                                                     ema, ema_decay, lp, nvec, bias_corr))
+                                                     ema, ema_decay, lp, nvec, bias_corr, zero_grad))
   if (ema && lp) FV_ADAM_LAUNCH(true, true);
   else if (ema) FV_ADAM_LAUNCH(true, false);
   else if (lp) FV_ADAM_LAUNCH(false, true);
@@ -258,23 +296,50 @@ static int adamw_flat_impl(float* p, const float* g, float* m, float* v, const i
 }
 }  // namespace fv
 
-extern "C" int fv_adamw_flat(float* p, const float* g, float* m, float* v, const int64_t* seg_end,
+extern "C" int fv_adamw_flat(float* p, float* g, float* m, float* v, const int64_t* seg_end,
                              const float* seg_lr, const float* seg_wd, int nseg, const float* sumsq,
                              float max_norm, float beta1, float beta2, float eps, int64_t step,
-                             float* ema, float ema_decay, void* p_lp, int64_t n, void* stream) {
+                             float* ema, float ema_decay, void* p_lp, int64_t n, int zero_grad, void* stream) {
   return fv::adamw_flat_impl(p, g, m, v, seg_end, seg_lr, seg_wd, nseg, sumsq, max_norm, beta1, beta2, eps, step,
-                             nullptr, ema, ema_decay, p_lp, n, stream);
+                             nullptr, ema, ema_decay, p_lp, n, zero_grad, stream);
 }
 
 // Same sweep with the two step-dependent scalars read from device memory — bias_corr[0] = 1 - beta1^t,
 // bias_corr[1] = sqrt(1 - beta2^t) — so a launch captured in a CUDA graph stays valid for every step t.
-extern "C" int fv_adamw_flat_dev(float* p, const float* g, float* m, float* v, const int64_t* seg_end,
+extern "C" int fv_adamw_flat_dev(float* p, float* g, float* m, float* v, const int64_t* seg_end,
                                  const float* seg_lr, const float* seg_wd, int nseg, const float* sumsq,
                                  float max_norm, float beta1, float beta2, float eps, const float* bias_corr,
-                                 float* ema, float ema_decay, void* p_lp, int64_t n, void* stream) {
+                                 float* ema, float ema_decay, void* p_lp, int64_t n, int zero_grad, void* stream) {
   FV_CHECK_ARG(bias_corr != nullptr, "fv_adamw_flat_dev: bias_corr is NULL");
   return fv::adamw_flat_impl(p, g, m, v, seg_end, seg_lr, seg_wd, nseg, sumsq, max_norm, beta1, beta2, eps, 0,
-                             bias_corr, ema, ema_decay, p_lp, n, stream);
+                             bias_corr, ema, ema_decay, p_lp, n, zero_grad, stream);
+}
+
+// Device-side step counter of the graph-replayed optimiser: *step += 1 and the two bias corrections of
+// that step into bias_corr[0..1], one thread. Captured in the CUDA graph right before the sweep, so
+// however far the host runs ahead of the device every replay sees exactly its own step (the host-written
+// pinned ring this replaces could be overwritten before its copy executed).
+namespace fv {
+__global__ void adamw_tick_kernel(long long* step, float* bias_corr, float beta1, float beta2) {
+  pdl_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long t = *step + 1;
+    *step = t;
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(t));
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(t));
+    bias_corr[0] = static_cast<float>(bc1);
+    bias_corr[1] = static_cast<float>(sqrt(bc2));
+  }
+}
+}  // namespace fv
+
+extern "C" int fv_adamw_tick(int64_t* step, float* bias_corr, float beta1, float beta2, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(step && bias_corr, "fv_adamw_tick: null pointer");
+  FV_CHECK_CUDA(fv::launch_pdl(adamw_tick_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream),
+                               reinterpret_cast<long long*>(step), bias_corr, beta1, beta2));
+  FV_LAUNCH_CHECK();
+  return FV_OK;
 }
 
 extern "C" int fv_scale_inplace(float* x, const float* sumsq, float max_norm, int64_t n, void* stream) {
@@ -307,6 +372,24 @@ extern "C" int fv_fedavg_accum(float* acc, const float* w, float weight, int ini
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (init) FV_CHECK_CUDA(fv::launch_pdl(fedavg_kernel<true>, dim3(sweep_grid(n >> 2)), dim3(SWEEP_THREADS), 0, st, acc, w, weight, n >> 2));
   else FV_CHECK_CUDA(fv::launch_pdl(fedavg_kernel<false>, dim3(sweep_grid(n >> 2)), dim3(SWEEP_THREADS), 0, st, acc, w, weight, n >> 2));
+  FV_LAUNCH_CHECK();
+  return FV_OK;
+}
+
+extern "C" int fv_fedavg_fold_into(const float* acc, const float* w, float weight, float* out, void* out_lp,
+                                   int64_t n, void* stream) {
+  using namespace fv;
+  FV_CHECK_ARG(w && out && n >= 0 && n % 4 == 0 && aligned16(w) && aligned16(out) && (!acc || aligned16(acc)) &&
+                   (!out_lp || (reinterpret_cast<uintptr_t>(out_lp) & 7) == 0),
+               "fv_fedavg_fold_into: bad argument");
+  if (n == 0) return FV_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(out_lp);
+  const dim3 grid(sweep_grid(n >> 2)), block(SWEEP_THREADS);
+  if (acc && lp) FV_CHECK_CUDA(fv::launch_pdl(fedavg_into_kernel<true, true>, grid, block, 0, st, acc, w, weight, out, lp, n >> 2));
+  else if (acc) FV_CHECK_CUDA(fv::launch_pdl(fedavg_into_kernel<true, false>, grid, block, 0, st, acc, w, weight, out, lp, n >> 2));
+  else if (lp) FV_CHECK_CUDA(fv::launch_pdl(fedavg_into_kernel<false, true>, grid, block, 0, st, acc, w, weight, out, lp, n >> 2));
+  else FV_CHECK_CUDA(fv::launch_pdl(fedavg_into_kernel<false, false>, grid, block, 0, st, acc, w, weight, out, lp, n >> 2));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

@@ -6,10 +6,16 @@ authored in SURVEY.md §8.2 / §8e (McMahan et al. 2017):
     w^{r+1} = sum_k (n_k / sum_j n_j) * w_k        over every floating-point entry of the state
 
 Data path per round, per GPU: each local client's trained weights are folded into an fp32
-accumulator with one HBM sweep (``fv_fedavg_accum``: 12 B/param, 8 for the first client), then ONE
-``ncclAllReduce(sum)`` over the flat buffer (345 MB for ViT-B, 1.22 GB for ViT-L) makes every rank
-hold w^{r+1}. Clients shard across GPUs round-robin (client k -> rank k mod G); there is no other
-collective on the path.
+accumulator with one HBM sweep (``fv_fedavg_accum``: 12 B/param, 8 for the first client); the LAST
+local client is folded straight into the parameter arena (``fv_fedavg_fold_into``), ONE
+``ncclAllReduce(sum)`` runs on that arena in place (345 MB for ViT-B, 1.22 GB for ViT-L) and the bf16
+shadow is re-cast — no accumulator -> arena copy, and with one client per GPU (BASELINE config 2) no
+snapshot of the global weights and no accumulator at all. There is no other collective on the path.
+
+Client placement: equal shards go round-robin (client k -> rank k mod G). Unequal shards
+(BASELINE config 4: 16 non-IID clients of 512 ... 2048 samples on 8 GPUs) are placed by
+longest-processing-time-first on n_k — a round lasts as long as its most loaded GPU — see
+``assign_clients``.
 
 Reduction order: within a rank, clients are folded in ascending id with one rounded multiply and
 one rounded add each (bit-identical to oracle/fedavg.py on a single GPU); across ranks the order is
@@ -33,8 +39,33 @@ def dist_info():
     return 0, 1
 
 
-def clients_of_rank(num_clients: int, rank: int, world: int) -> List[int]:
-    """Client k trains on GPU k mod G; several clients on one GPU run back to back."""
+def assign_clients(sizes: Sequence[int], world: int) -> List[List[int]]:
+    """Clients of every rank. Equal shard sizes: client k -> rank k mod G. Unequal
+    sizes: longest-processing-time-first — clients in descending n_k (ties: lower id first), each to
+    the rank with the least samples so far (ties: lowest rank) — because the round ends when the most
+    loaded GPU does. Deterministic, identical on every rank; within a rank clients run and are
+    folded in ascending id, so the single-GPU fold order (and its bit-exactness) is unchanged."""
+    k = len(sizes)
+    if world <= 1:
+        return [list(range(k))]
+    if len(set(int(s) for s in sizes)) <= 1:
+        return [[c for c in range(k) if c % world == r] for r in range(world)]
+    load = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for c in sorted(range(k), key=lambda c: (-int(sizes[c]), c)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        out[r].append(c)
+        load[r] += int(sizes[c])
+    return [sorted(cs) for cs in out]
+
+
+def clients_of_rank(num_clients: int, rank: int, world: int, sizes: Optional[Sequence[int]] = None) -> List[int]:
+    """Clients that train on GPU ``rank`` (several on one GPU run back to back): k mod G, or the
+    load-balanced placement of ``assign_clients`` when unequal shard sizes are given."""
+    if sizes is not None:
+        if len(sizes) != num_clients:
+            raise ValueError("sizes must have num_clients entries")
+        return assign_clients(sizes, world)[rank]
     return [k for k in range(num_clients) if k % world == rank]
 
 
@@ -46,15 +77,29 @@ def client_weight(n_k: int, n_total: int) -> float:
 class FedAvgAggregator:
     """Round protocol over one flat parameter buffer. ``fold`` is the HBM sweep
     (``ops.fedavg_accum`` — the CUDA kernel); it is a parameter only so the protocol and the
-    collective can be exercised by the CPU/gloo tests with a stand-in."""
+    collective can be exercised by the CPU/gloo tests with a stand-in.
+
+        agg.begin_round(n_local)               # n_local = clients this rank trains this round
+        for c in my_clients:
+            agg.load_global()                  # restart from w^r (free for the first client)
+            ... local epochs ...
+            agg.fold(n_c, n_total, c, last=c == my_clients[-1])
+        agg.finish(root=rank_of_client_0)      # one allreduce, in place on the parameter arena
+    """
 
     def __init__(self, model: nn.Module, arena, fold=None) -> None:
         self.model = model
         self.arena = arena
+        self._custom_fold = fold is not None
         self._fold = fold if fold is not None else ops.fedavg_accum
-        self.global_flat = arena.params.clone()
-        self.acc = torch.zeros_like(arena.params)
+        # allocated on first need: with one client per GPU neither exists (2 x 345 MB at ViT-B)
+        self.global_flat: Optional[torch.Tensor] = None
+        self.acc: Optional[torch.Tensor] = None
         self._folded = 0
+        self._loaded = 0
+        self._have_snapshot = False
+        self._in_params = False   # the weighted sum of this rank's clients already sits in arena.params
+        self._lp_written = False  # ... and its bf16 copy in arena.lp
         # floating-point buffers outside the arena (BatchNorm running stats of the metadata MLP)
         self._fbufs = [(n, b) for n, b in model.named_buffers() if b.is_floating_point()]
         self._ibufs = [(n, b) for n, b in model.named_buffers() if not b.is_floating_point()]
@@ -64,28 +109,59 @@ class FedAvgAggregator:
 
     # -- round protocol -----------------------------------------------------------------------
     @torch.no_grad()
-    def begin_round(self) -> None:
-        """Snapshot w^r: every client of this round starts from it."""
-        self.global_flat.copy_(self.arena.params)
+    def begin_round(self, n_local: Optional[int] = None) -> None:
+        """Start of round r; the arena holds w^r. A snapshot of it is only taken when a second local
+        client will have to restart from it (``n_local`` unknown or > 1)."""
+        self._have_snapshot = n_local is None or n_local > 1
+        if self._have_snapshot:
+            if self.global_flat is None:
+                self.global_flat = torch.empty_like(self.arena.params)
+            self.global_flat.copy_(self.arena.params)
         for g, (_, b) in zip(self._gbuf, self._fbufs):
             g.copy_(b)
         self._folded = 0
+        self._loaded = 0
+        self._in_params = False
+        self._lp_written = False
         self._ibuf0 = None
 
     @torch.no_grad()
     def load_global(self) -> None:
-        self.arena.params.copy_(self.global_flat)
+        """Reset the arena to w^r for the next local client. The first client of a round finds w^r
+        already there (nothing has trained since ``begin_round``): no copy, no re-cast."""
+        first = self._loaded == 0 and self._folded == 0
+        self._loaded += 1
         for g, (_, b) in zip(self._gbuf, self._fbufs):
             b.copy_(g)
+        if first:
+            return
+        if not self._have_snapshot:
+            raise RuntimeError("FedAvgAggregator: begin_round(n_local=1) took no snapshot of the global "
+                               "weights, but a second client asked for them")
+        self.arena.params.copy_(self.global_flat)
         if self.arena.lp is not None:
             self.arena.refresh_lp(force=True)
 
     @torch.no_grad()
-    def fold(self, n_k: int, n_total: int, client_id: int = 0) -> None:
-        """acc += (n_k / n_total) * w_k for the client whose weights are in the arena now."""
+    def fold(self, n_k: int, n_total: int, client_id: int = 0, last: bool = False) -> None:
+        """acc += (n_k / n_total) * w_k for the client whose weights are in the arena now. ``last``
+        (this rank's final client of the round): the sum is written into the parameter arena itself,
+        where ``finish`` reduces it in place."""
         w = client_weight(n_k, n_total)
         first = self._folded == 0
-        self._fold(self.acc, self.arena.params, w, first)
+        if self._in_params:
+            raise RuntimeError("FedAvgAggregator.fold: called after the round's last fold")
+        p = self.arena.params
+        if last and not self._custom_fold:
+            world = dist_info()[1]
+            lp = self.arena.lp if world == 1 else None  # across ranks the bf16 copy follows the allreduce
+            ops.fedavg_fold_into(None if first else self.acc, p, w, p, lp)
+            self._in_params = True
+            self._lp_written = lp is not None
+        else:
+            if self.acc is None:
+                self.acc = torch.empty_like(p)
+            self._fold(self.acc, p, w, first)
         for a, (_, b) in zip(self._accbuf, self._fbufs):
             t = b.to(torch.float32) * w
             if first:
@@ -97,30 +173,37 @@ class FedAvgAggregator:
         self._folded += 1
 
     @torch.no_grad()
-    def finish(self) -> None:
-        """Cross-GPU sum (one NCCL allreduce of the flat buffer) and install w^{r+1} everywhere."""
+    def finish(self, root: int = 0) -> None:
+        """Cross-GPU sum (one NCCL allreduce, in place on the parameter arena) and install of w^{r+1}
+        everywhere. ``root`` = the rank that trained client 0 (integer buffers come from it)."""
         rank, world = dist_info()
-        if self._folded == 0:
-            self.acc.zero_()
+        p = self.arena.params
+        if self._folded == 0:  # a rank without clients contributes zeros
+            p.zero_()
             for a in self._accbuf:
                 a.zero_()
+        elif not self._in_params:
+            p.copy_(self.acc)
         if world > 1:
-            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+            dist.all_reduce(p, op=dist.ReduceOp.SUM)
             for a in self._accbuf:
                 dist.all_reduce(a, op=dist.ReduceOp.SUM)
-            # integer buffers (num_batches_tracked) come from client 0 == rank 0's first client
+            # integer buffers (num_batches_tracked) come from client 0
             for i, (_, b) in enumerate(self._ibufs):
-                src = self._ibuf0[i] if (rank == 0 and self._ibuf0 is not None) else b.detach().clone()
-                dist.broadcast(src, src=0)
+                src = self._ibuf0[i] if (rank == root and self._ibuf0 is not None) else b.detach().clone()
+                dist.broadcast(src, src=root)
                 b.copy_(src)
         elif self._ibuf0 is not None:
             for (_, b), s in zip(self._ibufs, self._ibuf0):
                 b.copy_(s)
-        self.arena.params.copy_(self.acc)
         for a, (_, b) in zip(self._accbuf, self._fbufs):
             b.copy_(a.to(b.dtype))
         if self.arena.lp is not None:
-            self.arena.refresh_lp(force=True)
+            if self._lp_written and world == 1:
+                self.arena.mark_lp_fresh()
+            else:
+                self.arena.refresh_lp(force=True)
+        self._in_params = False
 
 
 @torch.no_grad()

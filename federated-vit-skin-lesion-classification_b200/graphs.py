@@ -128,6 +128,7 @@ class GraphedTrainStep:
             for b, saved in zip(self.model.buffers(), snap["buffers"]):
                 b.copy_(saved)
         opt.step_count = snap["step"]
+        opt._set_device_step(snap["step"])
         opt._tick_pending = False
         torch.cuda.set_rng_state(snap["rng"], arena.device)
         if arena.lp is not None:
@@ -156,8 +157,11 @@ class GraphedTrainStep:
             # parameters written through PyTorch since the last step (a FedAvg install, a checkpoint load):
             # the captured forward reads the bf16 shadow as it finds it, so bring it up to date here
             arena.refresh_lp()
+        if not arena.grads_clean:  # the captured zero_grad was a no-op (the sweep before it leaves zeros)
+            arena.zero_grads()
         self.optimizer.graph_tick()
         self.graph.replay()
+        arena.grads_clean = bool(getattr(self.optimizer, "fuse_zero_grad", False))
         self.optimizer._tick_pending = False  # consumed by the replayed sweep
         if self.optimizer.ema is not None:  # the replayed sweep updated the shadow (utils.EMA.update() then skips)
             self.optimizer.ema._fused_updates += 1

@@ -407,6 +407,23 @@ def cls_pos_rows(cls: Tensor, pos: Tensor, x: Tensor, batch: int, tokens: int, d
     LIB.call("fv_cls_pos_rows", cls.data_ptr(), pos.data_ptr(), x.data_ptr(), batch, tokens, dim, _stream(x))
 
 
+@_op("fedvit::cls_grad_rows", mutates_args=("dx", "dy"))
+def cls_grad_rows(dcls: Tensor, row_scale: Optional[Tensor], dx: Optional[Tensor], dy: Optional[Tensor],
+                  batch: int, tokens: int, dim: int) -> None:
+    """Head of the backbone backward: ``dx`` / ``dy`` [B*N, D] are zero except row 0 of each image
+    (= dcls, ``dy`` times the per-sample ``row_scale``) — one pass instead of zeros + assign + cast."""
+    _need_cuda(dcls, row_scale, dx, dy)
+    if dcls.dtype != torch.float32 or not dcls.is_contiguous() or tuple(dcls.shape) != (batch, dim):
+        raise FedVitError("cls_grad_rows: dcls must be contiguous fp32 [B, D]")
+    for t in (dx, dy):
+        if t is not None and (not t.is_contiguous() or t.numel() != batch * tokens * dim):
+            raise FedVitError("cls_grad_rows: outputs must be contiguous [B*N, D]")
+    if dx is not None and dx.dtype != torch.float32:
+        raise FedVitError("cls_grad_rows: dx is fp32")
+    LIB.call("fv_cls_grad_rows", dcls.data_ptr(), _ptr(row_scale), _ptr(dx), _ptr(dy),
+             _dt(dy) if dy is not None else F32, batch, tokens, dim, _stream(dcls))
+
+
 @_op("fedvit::colsum", mutates_args=("out",))
 def colsum(a: Tensor, out: Tensor, accumulate: bool) -> None:
     """out[c] (+)= sum_r a[r, c] — bias / pos_embed / cls_token gradients."""
@@ -423,7 +440,9 @@ def colsum(a: Tensor, out: Tensor, accumulate: bool) -> None:
 @_op("fedvit::asl_loss", mutates_args=())
 def asl_loss(logits: Tensor, targets: Tensor, gamma_neg: float, gamma_pos: float, clip: float,
              eps: float) -> Tuple[Tensor, Tensor]:
-    """(mean asymmetric-focal loss [scalar], d loss / d logits [B,C]) in one fused pass."""
+    """(mean asymmetric-focal loss [scalar], d loss / d logits [B,C]) in one fused pass. A target outside
+    [0, C) — where the reference's F.one_hot raises (losses.py:47) — yields a NaN loss (a kernel cannot
+    raise and a host-side range check would cost a device sync per step)."""
     _need_cuda(logits, targets)
     logits = logits.float().contiguous()
     targets = targets.to(torch.int64).contiguous()
@@ -466,23 +485,25 @@ def sumsq(g: Tensor, out: Tensor, accumulate: bool) -> None:
     LIB.call("fv_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), int(accumulate), _stream(g))
 
 
-@_op("fedvit::adamw_flat", mutates_args=("p", "m", "v", "ema", "p_lp"))
+@_op("fedvit::adamw_flat", mutates_args=("p", "g", "m", "v", "ema", "p_lp"))
 def adamw_flat(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_lr: Tensor,
                seg_wd: Tensor, sumsq_: Optional[Tensor], max_norm: float, beta1: float, beta2: float,
                eps: float, step: int, ema: Optional[Tensor], ema_decay: float,
-               p_lp: Optional[Tensor]) -> None:
+               p_lp: Optional[Tensor], zero_grad: bool = False) -> None:
+    """One sweep: clip coefficient, AdamW over the per-range lr / weight-decay table, optional EMA and
+    bf16 re-cast; ``zero_grad`` leaves ``g`` zeroed behind the sweep (its last reader)."""
     _need_cuda(p, g, m, v, seg_end, seg_lr, seg_wd, sumsq_, ema, p_lp)
     LIB.call("fv_adamw_flat", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
              seg_end.data_ptr(), seg_lr.data_ptr(), seg_wd.data_ptr(), seg_end.numel(),
              _ptr(sumsq_), max_norm, beta1, beta2, eps, step, _ptr(ema), ema_decay, _ptr(p_lp),
-             p.numel(), _stream(p))
+             p.numel(), int(zero_grad), _stream(p))
 
 
-@_op("fedvit::adamw_flat_dev", mutates_args=("p", "m", "v", "ema", "p_lp"))
+@_op("fedvit::adamw_flat_dev", mutates_args=("p", "g", "m", "v", "ema", "p_lp"))
 def adamw_flat_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_lr: Tensor,
                    seg_wd: Tensor, sumsq_: Optional[Tensor], max_norm: float, beta1: float, beta2: float,
                    eps: float, bias_corr: Tensor, ema: Optional[Tensor], ema_decay: float,
-                   p_lp: Optional[Tensor]) -> None:
+                   p_lp: Optional[Tensor], zero_grad: bool = False) -> None:
     """``adamw_flat`` with the step-dependent bias corrections ``[1 - beta1^t, sqrt(1 - beta2^t)]`` in a
     device tensor instead of the step number as a launch argument (CUDA-graph replay)."""
     _need_cuda(p, g, m, v, seg_end, seg_lr, seg_wd, sumsq_, bias_corr, ema, p_lp)
@@ -491,7 +512,17 @@ def adamw_flat_dev(p: Tensor, g: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, 
     LIB.call("fv_adamw_flat_dev", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
              seg_end.data_ptr(), seg_lr.data_ptr(), seg_wd.data_ptr(), seg_end.numel(),
              _ptr(sumsq_), max_norm, beta1, beta2, eps, bias_corr.data_ptr(), _ptr(ema), ema_decay,
-             _ptr(p_lp), p.numel(), _stream(p))
+             _ptr(p_lp), p.numel(), int(zero_grad), _stream(p))
+
+
+@_op("fedvit::adamw_tick", mutates_args=("step", "bias_corr"))
+def adamw_tick(step: Tensor, bias_corr: Tensor, beta1: float, beta2: float) -> None:
+    """Device-side step counter of the graph-replayed optimiser: ``step += 1`` and that step's bias
+    corrections into ``bias_corr`` — captured in the graph right before ``adamw_flat_dev``."""
+    _need_cuda(step, bias_corr)
+    if step.dtype != torch.int64 or step.numel() != 1 or bias_corr.dtype != torch.float32 or bias_corr.numel() < 2:
+        raise FedVitError("adamw_tick: step int64 [1], bias_corr fp32 [2]")
+    LIB.call("fv_adamw_tick", step.data_ptr(), bias_corr.data_ptr(), beta1, beta2, _stream(step))
 
 
 @_op("fedvit::scale_by_clip", mutates_args=("x",))
@@ -513,6 +544,19 @@ def fedavg_accum(acc: Tensor, w: Tensor, weight: float, init: bool) -> None:
     if acc.dtype != torch.float32 or w.dtype != torch.float32 or acc.numel() != w.numel():
         raise FedVitError("fedavg_accum: fp32 arenas of equal length required")
     LIB.call("fv_fedavg_accum", acc.data_ptr(), w.data_ptr(), weight, int(init), w.numel(), _stream(w))
+
+
+@_op("fedvit::fedavg_fold_into", mutates_args=("out", "out_lp"))
+def fedavg_fold_into(acc: Optional[Tensor], w: Tensor, weight: float, out: Tensor, out_lp: Optional[Tensor]) -> None:
+    """out = (acc if given else 0) + weight * w, same rounding as ``fedavg_accum``; ``out`` may be ``w``
+    itself (the round's last fold lands in the parameter arena); optional bf16 copy of the result."""
+    _need_cuda(acc, w, out, out_lp)
+    if w.dtype != torch.float32 or out.dtype != torch.float32 or out.numel() != w.numel() or \
+            (acc is not None and (acc.dtype != torch.float32 or acc.numel() != w.numel())):
+        raise FedVitError("fedavg_fold_into: fp32 arenas of equal length required")
+    if out_lp is not None and (out_lp.dtype != torch.bfloat16 or out_lp.numel() != w.numel()):
+        raise FedVitError("fedavg_fold_into: out_lp must be a bf16 arena of the same length")
+    LIB.call("fv_fedavg_fold_into", _ptr(acc), w.data_ptr(), weight, out.data_ptr(), _ptr(out_lp), w.numel(), _stream(w))
 
 
 @_op("fedvit::cast_bf16", mutates_args=("dst",))

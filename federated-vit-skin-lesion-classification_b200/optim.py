@@ -30,7 +30,8 @@ def grad_sumsq(arena: FlatArena, out: Optional[torch.Tensor] = None) -> torch.Te
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, arena: Optional[FlatArena] = None) -> None:
+                 weight_decay: float = 1e-2, arena: Optional[FlatArena] = None,
+                 fuse_zero_grad: bool = True) -> None:
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         if arena is None:
@@ -56,9 +57,12 @@ class FusedAdamW(torch.optim.Optimizer):
         self._seg = None
         # CUDA-graph mode (graphs.GraphedTrainStep): the bias corrections of the current step live in a
         # device tensor that graph_tick() refreshes before every replay
-        self._bias_corr = None      # device fp32 [2]
-        self._bias_corr_host = None  # pinned ring the refresh copies from
+        self._bias_corr = None      # device fp32 [2]: bias corrections of the current step
+        self._step_dev = None       # device int64 [1]: the step counter the captured tick kernel advances
         self._tick_pending = False   # graph_tick() ran and no step has consumed it yet
+        # the sweep is the gradient buffer's last reader: it writes zeros back, and the zero_grad() that
+        # follows every step in the reference loop (train.py:160) finds the buffer clean — no memset pass
+        self.fuse_zero_grad = bool(fuse_zero_grad)
 
     # -- CUDA-graph support ---------------------------------------------------------------------------
     def enable_graph_mode(self) -> None:
@@ -69,23 +73,26 @@ class FusedAdamW(torch.optim.Optimizer):
         changes it, so its device addresses stay valid inside a captured graph."""
         if self._bias_corr is None:
             self._bias_corr = torch.ones(2, device=self.arena.device, dtype=torch.float32)
-            self._bias_corr_host = torch.ones((8, 2), dtype=torch.float32).pin_memory()
+            self._step_dev = torch.full((1,), self.step_count, device=self.arena.device, dtype=torch.int64)
             self._seg_key, self._seg = None, None  # rebuilt per param group: fixed length from here on
             self._segments()
 
     def graph_tick(self) -> None:
-        """Advance to the next optimisation step: step count, bias corrections -> device, and the lr table
-        if a scheduler moved it. Stream-ordered, no host sync (the pinned slot is reused 8 steps later)."""
+        """Host-side bookkeeping of the next optimisation step: the step count mirrored for checkpoints and
+        the lr table if a scheduler moved it. The step-dependent numbers the sweep needs never leave the
+        device: a one-thread kernel captured in the graph right before the sweep (``fv_adamw_tick``)
+        increments a device counter and derives the bias corrections from it, so a host that runs any
+        number of replays ahead of the GPU cannot hand a replay another step's corrections (the pinned
+        ring this replaces was overwritten after 8 un-synchronised steps)."""
         if self._bias_corr is None:
             raise RuntimeError("graph_tick() needs enable_graph_mode()")
         self.step_count += 1
-        b1, b2 = self.defaults["betas"]
-        slot = self._bias_corr_host[self.step_count % 8]
-        slot[0] = 1.0 - b1 ** self.step_count
-        slot[1] = (1.0 - b2 ** self.step_count) ** 0.5
-        self._bias_corr.copy_(slot, non_blocking=True)
         self._segments()
         self._tick_pending = True
+
+    def _set_device_step(self, step: int) -> None:
+        if self._step_dev is not None:
+            self._step_dev.fill_(int(step))
 
     # -- hooks used by utils.clip_grad_norm / utils.EMA -------------------------------------------
     def defer_clip(self, sumsq: torch.Tensor, max_norm: float) -> None:
@@ -144,14 +151,19 @@ class FusedAdamW(torch.optim.Optimizer):
                     self.graph_tick()
                     seg_end, seg_lr, seg_wd = self._seg
                 self._tick_pending = False
+            ops.adamw_tick(self._step_dev, self._bias_corr, b1, b2)
             ops.adamw_flat_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, seg_end, seg_lr, seg_wd,
                                sumsq, max_norm, b1, b2, self.defaults["eps"], self._bias_corr,
-                               ema.flat if ema is not None else None, ema.decay if ema is not None else 0.0, a.lp)
+                               ema.flat if ema is not None else None, ema.decay if ema is not None else 0.0, a.lp,
+                               self.fuse_zero_grad)
         else:
             self.step_count += 1
             ops.adamw_flat(a.params, a.grads, self.exp_avg, self.exp_avg_sq, seg_end, seg_lr, seg_wd,
                            sumsq, max_norm, b1, b2, self.defaults["eps"], self.step_count,
-                           ema.flat if ema is not None else None, ema.decay if ema is not None else 0.0, a.lp)
+                           ema.flat if ema is not None else None, ema.decay if ema is not None else 0.0, a.lp,
+                           self.fuse_zero_grad)
+        if self.fuse_zero_grad:
+            a.grads_clean = True
         if a.lp is not None:
             a.mark_lp_fresh()
         if ema is not None:
@@ -161,7 +173,11 @@ class FusedAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True) -> None:
         """One memset of the flat gradient buffer. Gradients stay attached as arena views even
         for ``set_to_none=True`` (the reference passes it, train.py:160): the kernels accumulate
-        into those views, which is what makes the single-sweep step possible."""
+        into those views, which is what makes the single-sweep step possible. Right after a ``step()`` the
+        buffer is already zero (the sweep wrote the zeros behind its last read) and nothing is launched.
+        A clip coefficient deferred by ``utils.clip_grad_norm`` that no ``step()`` consumed is dropped
+        here: it belongs to the gradients being discarded."""
+        self._pending_clip = None
         self.arena.zero_grads()
 
     # -- checkpoint interchange: moments are exposed per parameter like torch.optim.AdamW ----------
@@ -197,9 +213,11 @@ class FusedAdamW(torch.optim.Optimizer):
                     self.step_count = int(float(s["step"]))
                 idx += 1
         self._seg_key = None
+        self._set_device_step(self.step_count)
 
     def reset_state(self) -> None:
         """Fresh moments and step count — the per-round client reset of canonical FedAvg."""
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         self.step_count = 0
+        self._set_device_step(0)

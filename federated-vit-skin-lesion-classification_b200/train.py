@@ -39,7 +39,7 @@ import torch.nn as nn
 
 from .arena import FlatArena
 from .data import SyntheticClientLoader, client_label_probs, client_sizes
-from .fedavg import FedAvgAggregator, broadcast_initial, clients_of_rank, dist_info
+from .fedavg import FedAvgAggregator, assign_clients, broadcast_initial, dist_info
 from .losses import build_loss
 from .model import build_model, count_parameters, get_layerwise_lr_groups
 from .optim import FusedAdamW
@@ -337,7 +337,20 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
                   loaders: Optional[Dict[int, SyntheticClientLoader]] = None, val_loader=None,
                   device_resident: bool = False) -> dict:
     """FedAvg over ``federated.num_clients`` clients for ``federated.rounds`` rounds. Returns the
-    per-round records (wall time from CUDA events, images/s, mean client loss, allreduce time)."""
+    per-round records (wall time from CUDA events, images/s, mean client loss, allreduce time, every
+    rank's busy time).
+
+    Policies the reference cannot supply (it has no federated loop):
+      * client optimiser state (AdamW moments, step count) is reset for every client, every round;
+      * the lr schedule is stepped once per round (train.py:297 steps it once per epoch) — with
+        ``scheduler.warmup_epochs > 0`` the reference's formula starts at lr = 0 (utils.py:179-185), so the
+        first ROUND trains at lr 0, as the reference's first epoch does;
+      * ``training.ema`` is a SERVER-side average here: one shadow of the GLOBAL weights, updated once per
+        round from w^{r+1} after the aggregate (``decay`` applies per round) and used for validation.
+        A client-side shadow carried across clients and rounds while ``load_global`` resets the weights
+        under it would blend unrelated trajectories and differ from rank to rank;
+      * clients are placed by ``fedavg.assign_clients`` (round-robin for equal shards, longest-processing-
+        time-first on n_k otherwise)."""
     fed = config.get("federated", {})
     t = config.get("training", {})
     rank, world = dist_info()
@@ -359,13 +372,16 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
     scheduler = WarmupCosineScheduler(optimizer, warmup_epochs=sched_cfg.get("warmup_epochs", 0),
                                       total_epochs=max(rounds, 1), min_lr=sched_cfg.get("min_lr", 1e-6))
     ema_cfg = t.get("ema", {})
-    ema = EMA(model, decay=ema_cfg.get("decay", 0.9995)).attach(optimizer) if ema_cfg.get("enabled", False) else None
+    # server-side EMA of the global model (see the docstring): NOT attached to the client optimiser
+    ema = EMA(model, decay=ema_cfg.get("decay", 0.9995)) if ema_cfg.get("enabled", False) else None
     scaler = torch.amp.GradScaler(device.type, enabled=False)  # bf16: no loss scaling
     criterion = build_loss(config).to(device)
 
     sizes = client_sizes(config)
     n_total = sum(sizes)
-    mine = clients_of_rank(len(sizes), rank, world)
+    placement = assign_clients(sizes, world)
+    mine = placement[rank]
+    root = next(r for r, cs in enumerate(placement) if 0 in cs)  # integer buffers come from client 0
     if loaders is None:
         loaders = build_client_loaders(config, mine, device_resident, device)
     agg = FedAvgAggregator(model, arena)
@@ -381,24 +397,29 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
             dist.barrier()
         torch.cuda.synchronize(device)
         ev[0].record()
-        agg.begin_round()
+        agg.begin_round(len(mine))
         losses = []
         for c in mine:
             agg.load_global()
             optimizer.reset_state()  # canonical FedAvg: client optimiser state does not survive the round
             for e in range(local_epochs):
                 losses.append(train_one_epoch(model, loaders[c], criterion, optimizer, scheduler, scaler,
-                                              ema, device, config, e + 1, logger))
-            agg.fold(sizes[c], n_total, client_id=c)
+                                              None, device, config, e + 1, logger))
+            agg.fold(sizes[c], n_total, client_id=c, last=c == mine[-1])
         ev[1].record()
-        agg.finish()
+        agg.finish(root=root)
+        if ema is not None:
+            ema.update()  # shadow <- decay * shadow + (1 - decay) * w^{r+1}: identical on every rank
         ev[2].record()
         torch.cuda.synchronize(device)
         scheduler.step()
         ms = torch.tensor([ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[2])], device=device)
+        busy = torch.tensor([ev[0].elapsed_time(ev[1])], device=device)  # this rank's local training + folds
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        images = n_total * local_epochs  # all ranks together (drop_last: whole batches only)
+            all_busy = [torch.zeros_like(busy) for _ in range(world)]
+            dist.all_gather(all_busy, busy)
+            busy = torch.cat(all_busy)
         images = sum((s // int(t.get("batch_size", 16))) * int(t.get("batch_size", 16)) for s in sizes) * local_epochs
         # sample-weighted mean of the clients' epoch losses over ALL ranks (logging only)
         lw = torch.tensor([sum(l * sizes[c] for l, c in zip(losses[local_epochs - 1::local_epochs], mine)),
@@ -407,7 +428,8 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
             dist.all_reduce(lw)
         rec = {"round": rnd, "round_ms": float(ms[0]), "aggregate_ms": float(ms[1]),
                "images_per_s": images / (float(ms[0]) / 1e3),
-               "mean_client_loss": float(lw[0] / lw[1]) if float(lw[1]) > 0 else None}
+               "mean_client_loss": float(lw[0] / lw[1]) if float(lw[1]) > 0 else None,
+               "rank_busy_ms": [float(v) for v in busy.tolist()]}
         if val_loader is not None:
             if ema is not None:
                 ema.apply_shadow()
@@ -418,7 +440,7 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
         if rank == 0:
             logger.info(f"  round {rnd:02d} | {rec['round_ms']:.1f} ms | {rec['images_per_s']:.0f} img/s | "
                         f"aggregate {rec['aggregate_ms']:.2f} ms | loss {rec['mean_client_loss']}")
-    return {"rounds": records, "model": model, "arena": arena}
+    return {"rounds": records, "model": model, "arena": arena, "ema": ema, "placement": placement}
 
 
 def main() -> None:

@@ -110,8 +110,10 @@ class Block(nn.Module):
 def _grad_buffer(p: nn.Parameter) -> Tensor:
     """Where this parameter's gradient is accumulated. Creates (zeroed) ``p.grad`` on first use;
     inside a FlatArena that is the parameter's slice of the flat gradient buffer."""
+    a = getattr(p, "_fv_arena", None)
+    if a is not None:
+        a[0].grads_clean = False  # something is about to be accumulated into the flat gradient buffer
     if p.grad is None:
-        a = getattr(p, "_fv_arena", None)
         if a is not None and a[0].owns(p):
             g = a[0].grad_view(p)
             g.zero_()
@@ -241,6 +243,9 @@ class VisionTransformer(nn.Module):
         params = self._bb_params()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if need_grad:
+            a = getattr(self.cls_token, "_fv_arena", None)
+            if a is not None:  # autograd-side modules (metadata MLP) accumulate into arena views too
+                a[0].grads_clean = False
             return _VitFunction.apply(self, x.float(), lp, *params)
         feats, _ = self._forward_impl(x.float(), lp, save=False)
         return feats
@@ -426,14 +431,16 @@ class VisionTransformer(nn.Module):
             dyf = dcls * last_s2.view(B, 1) if last_s2 is not None else dcls
             dy = _to_bf16(dyf) if lp else dyf
         else:
-            dx = torch.zeros((M, D), device=dev, dtype=torch.float32)
-            dx.view(B, N, D)[:, 0] = dcls
-            if last_s2 is not None:  # the last block's MLP branch carried a stochastic-depth factor
-                dyf = dx.clone()
-                dyf.view(B, N, D)[:, 0] *= last_s2.view(B, 1)
-                dy = _to_bf16(dyf) if lp else dyf
+            # one pass writes both the fp32 residual-path gradient and the operand of the last block's
+            # fc2 gradients (bf16 under autocast; times that block's stochastic-depth factor): zero
+            # everywhere except the cls rows
+            dx = torch.empty((M, D), device=dev, dtype=torch.float32)
+            if lp or last_s2 is not None:
+                dy = torch.empty((M, D), device=dev, dtype=torch.bfloat16 if lp else torch.float32)
+                ops.cls_grad_rows(dcls, last_s2, dx, dy, B, N, D)
             else:
-                dy = _to_bf16(dx) if lp else dx
+                ops.cls_grad_rows(dcls, None, dx, None, B, N, D)
+                dy = dx
 
         nblk = len(st.blocks)
         for i in range(nblk - 1, -1, -1):

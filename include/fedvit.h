@@ -54,6 +54,17 @@ int fv_version(void);
 const char* fv_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t fv_launch_count(void);
+/* launches per kernel family since load — lets a test assert WHICH kernel served a call (e.g. that a
+ * ViT-B step really ran on the CTA-pair GEMM) without a profiler attached */
+#define FV_KERNEL_GEMM_TC 0        /* single-CTA tcgen05 GEMM                     */
+#define FV_KERNEL_GEMM_TC_PAIR 1   /* CTA-pair (cta_group::2) tcgen05 GEMM        */
+#define FV_KERNEL_ATTN_FWD 2       /* tcgen05 attention forward, N <= 256         */
+#define FV_KERNEL_ATTN_BWD 3       /* tcgen05 attention backward, N <= 256        */
+#define FV_KERNEL_ATTN_FWD_LONG 4  /* tcgen05 attention forward, 256 < N <= 768   */
+#define FV_KERNEL_ATTN_BWD_LONG 5  /* tcgen05 attention backward, 256 < N <= 768  */
+#define FV_KERNEL_ATTN_LEGACY 6    /* mma.sync flash kernels (N > 768)            */
+#define FV_KERNEL_FAMILIES 8
+int64_t fv_kernel_launches(int family);
 
 /* ------------------------------------------------------------------------------------------
  * GEMM  C[M,N] = op(A)[M,K] * op(B)[N,K]^T  with a fused epilogue.
@@ -169,6 +180,13 @@ int fv_patchify(const float* img, void* out, int out_dtype,
 int fv_cls_pos_rows(const float* cls, const float* pos, float* x,
                     int64_t batch, int64_t tokens, int64_t dim, void* stream);
 
+/* Head of the backbone backward (the head reads timm's global_pool='token' only, model.py:193):
+ *   dx[b*tokens + t, :] = t == 0 ? dcls[b, :] : 0                    (fp32, may be NULL)
+ *   dy[b*tokens + t, :] = t == 0 ? dcls[b, :] * row_scale[b] : 0     (dy_dtype, may be NULL)
+ * row_scale = the last block's per-sample stochastic-depth factor (NULL: 1).                   */
+int fv_cls_grad_rows(const float* dcls, const float* row_scale, float* dx, void* dy, int dy_dtype,
+                     int64_t batch, int64_t tokens, int64_t dim, void* stream);
+
 /* column sums: out[n] (+)= sum_m a[m,n]   (bias gradients, pos_embed / cls_token gradients)   */
 int fv_colsum(const void* a, int a_dtype, int64_t lda, float* out, int accumulate,
               int64_t rows, int64_t cols, void* stream);
@@ -219,21 +237,26 @@ int fv_ce_loss(const float* logits, const int64_t* targets, float* loss, float* 
  *   step     : 1-based step count for bias correction
  *   ema/ema_decay : optional shadow arena (NULL to skip)
  *   p_lp     : optional bf16 copy of the updated parameters (NULL to skip)
+ *   zero_grad: non-zero -> the sweep, the gradient's last reader, writes zeros back into g: the
+ *              optimizer.zero_grad of the next step (train.py:160) costs no pass of its own
  * ---------------------------------------------------------------------------------------- */
 int fv_sumsq(const float* g, int64_t n, float* sumsq, int accumulate, void* stream);
-int fv_adamw_flat(float* p, const float* g, float* m, float* v,
+int fv_adamw_flat(float* p, float* g, float* m, float* v,
                   const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int nseg,
                   const float* sumsq, float max_norm, float beta1, float beta2, float eps,
                   int64_t step, float* ema, float ema_decay, void* p_lp,
-                  int64_t n, void* stream);
+                  int64_t n, int zero_grad, void* stream);
 /* The same sweep with the two step-dependent scalars in DEVICE memory — bias_corr[0] = 1 - beta1^t,
- * bias_corr[1] = sqrt(1 - beta2^t), written by the host before each step — so a launch captured in a
- * CUDA graph (fedvit_b200.graphs.GraphedTrainStep) replays correctly for every step t. */
-int fv_adamw_flat_dev(float* p, const float* g, float* m, float* v,
+ * bias_corr[1] = sqrt(1 - beta2^t) — so a launch captured in a CUDA graph
+ * (fedvit_b200.graphs.GraphedTrainStep) replays correctly for every step t. fv_adamw_tick is the
+ * captured launch that advances them: *step += 1, bias_corr <- the corrections of that step (device
+ * arithmetic in fp64, one thread), so a replay never depends on host writes racing the device. */
+int fv_adamw_flat_dev(float* p, float* g, float* m, float* v,
                       const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int nseg,
                       const float* sumsq, float max_norm, float beta1, float beta2, float eps,
                       const float* bias_corr, float* ema, float ema_decay, void* p_lp,
-                      int64_t n, void* stream);
+                      int64_t n, int zero_grad, void* stream);
+int fv_adamw_tick(int64_t* step, float* bias_corr, float beta1, float beta2, void* stream);
 int fv_scale_inplace(float* x, const float* sumsq, float max_norm, int64_t n, void* stream);
 int fv_ema_update(float* shadow, const float* p, float decay, int64_t n, void* stream);
 int fv_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
@@ -245,6 +268,11 @@ int fv_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
  * The cross-GPU sum is an NCCL allreduce issued by the host (torch.distributed).
  * ---------------------------------------------------------------------------------------- */
 int fv_fedavg_accum(float* acc, const float* w, float weight, int init, int64_t n, void* stream);
+/* The last fold of a round: out = (acc ? acc : 0) + weight * w with the same rounding, where out may
+ * alias w — the result lands in the parameter arena the allreduce then runs on in place (no copy of
+ * the accumulator back) — and out_lp (optional) receives its bf16 copy (single-rank rounds).      */
+int fv_fedavg_fold_into(const float* acc, const float* w, float weight, float* out, void* out_lp,
+                        int64_t n, void* stream);
 
 /* fp32 attention helpers for the parity path: row softmax fwd/bwd on [rows, cols] scores      */
 int fv_softmax_rows(const float* s, float* p, int64_t rows, int64_t cols, float scale, void* stream);

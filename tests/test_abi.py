@@ -11,7 +11,8 @@ def test_header_parses_and_lists_the_path():
     protos = _lib.parse_header()
     for name in ["fv_gemm_bf16", "fv_gemm_f32", "fv_layernorm_fwd", "fv_layernorm_bwd", "fv_attention_fwd",
                  "fv_attention_bwd", "fv_asl_loss", "fv_ce_loss", "fv_adamw_flat", "fv_sumsq",
-                 "fv_fedavg_accum", "fv_patchify", "fv_colsum", "fv_assemble_batch", "fv_mix_batch", "fv_last_error",
+                 "fv_fedavg_accum", "fv_fedavg_fold_into", "fv_adamw_tick", "fv_cls_grad_rows",
+                 "fv_kernel_launches", "fv_patchify", "fv_colsum", "fv_assemble_batch", "fv_mix_batch", "fv_last_error",
                  "fv_launch_count"]:
         assert name in protos, name
     # plain C only: no C++ / torch types may appear in any signature

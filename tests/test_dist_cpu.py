@@ -28,7 +28,7 @@ def _cpu_fold(acc, w, weight, init):
         acc.add_(term)
 
 
-def _worker(rank, world, port, n_clients, tmp):
+def _worker(rank, world, port, n_clients, tmp, lpt=False):
     sys.path.insert(0, str(ROOT))
     import fedvit_b200  # noqa: F401
     from fedvit_b200 import fedavg
@@ -38,31 +38,35 @@ def _worker(rank, world, port, n_clients, tmp):
     try:
         n = 4099
         sizes = [64 * (1 + (k % 3)) for k in range(n_clients)]
+        if lpt:  # unequal shards placed by longest-processing-time-first; client 0 may land on any rank
+            sizes = [64 * (1 + (7 * k + 3) % 5) for k in range(n_clients)]
+        place = fedavg.assign_clients(sizes, world) if lpt else [fedavg.clients_of_rank(n_clients, r, world) for r in range(world)]
+        root = next(r for r, cs in enumerate(place) if 0 in cs)
         model = torch.nn.BatchNorm1d(4)  # float buffers (running stats) + an integer buffer
         arena = _Arena(n)
         g0 = torch.Generator().manual_seed(7)
         arena.params.copy_(torch.randn(n, generator=g0) if rank == 0 else torch.zeros(n))
         fedavg.broadcast_initial(arena, model)
         agg = fedavg.FedAvgAggregator(model, arena, fold=_cpu_fold)
-        agg.begin_round()
-        for c in fedavg.clients_of_rank(n_clients, rank, world):
+        agg.begin_round(len(place[rank]))
+        for c in place[rank]:
             agg.load_global()
             g = torch.Generator().manual_seed(100 + c)
             arena.params.add_(torch.randn(n, generator=g) * 0.1)  # "local training" of client c
             model.running_mean.fill_(float(c))
             model.num_batches_tracked.fill_(c + 5)
-            agg.fold(sizes[c], sum(sizes), client_id=c)
-        agg.finish()
+            agg.fold(sizes[c], sum(sizes), client_id=c, last=c == place[rank][-1])
+        agg.finish(root=root)
         torch.save({"params": arena.params.clone(), "rm": model.running_mean.clone(),
                     "nbt": model.num_batches_tracked.clone(), "sizes": sizes}, f"{tmp}/r{rank}.pt")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_clients", [2, 5])
-def test_fedavg_round_two_ranks_gloo(tmp_path, n_clients):
-    port = 29500 + os.getpid() % 2000 + n_clients
-    mp.spawn(_worker, args=(2, port, n_clients, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("n_clients,lpt", [(2, False), (5, False), (5, True)])
+def test_fedavg_round_two_ranks_gloo(tmp_path, n_clients, lpt):
+    port = 29500 + os.getpid() % 2000 + n_clients + (7 if lpt else 0)
+    mp.spawn(_worker, args=(2, port, n_clients, str(tmp_path), lpt), nprocs=2, join=True)
     r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
     assert torch.equal(r0["params"], r1["params"])  # every rank holds the same w^{r+1}
     sys.path.insert(0, str(ROOT))

@@ -155,6 +155,16 @@ def test_client_partition_and_weights():
     assert fedavg.clients_of_rank(8, 0, 8) == [0] and fedavg.clients_of_rank(16, 3, 8) == [3, 11]
     assert sorted(sum((fedavg.clients_of_rank(16, r, 4) for r in range(4)), [])) == list(range(16))
     assert fedavg.clients_of_rank(2, 0, 1) == [0, 1]
+    # unequal shards: longest-processing-time-first, deterministic, ascending ids within a rank
+    sizes = [512, 640, 768, 896, 1024, 1152, 1280, 1408, 1536, 1664, 1792, 1920, 2048, 512, 1024, 2048]
+    place = fedavg.assign_clients(sizes, 8)
+    assert place == fedavg.assign_clients(sizes, 8) and all(cs == sorted(cs) for cs in place)
+    assert sorted(sum(place, [])) == list(range(16))
+    loads = [sum(sizes[c] for c in cs) for cs in place]
+    assert max(loads) <= 1.06 * sum(sizes) / 8
+    assert max(sum(sizes[c] for c in range(16) if c % 8 == r) for r in range(8)) > 1.3 * sum(sizes) / 8
+    assert fedavg.clients_of_rank(16, 2, 8, sizes) == place[2]
+    assert fedavg.assign_clients([64] * 16, 8)[3] == [3, 11] and fedavg.assign_clients(sizes, 1) == [list(range(16))]
     from oracle import fedavg as ofed
     n_k = [512, 2048, 700, 1024]
     assert [fedavg.client_weight(n, sum(n_k)) for n in n_k] == ofed.client_weights(n_k)
