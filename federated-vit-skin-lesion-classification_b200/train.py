@@ -405,8 +405,11 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
             for e in range(local_epochs):
                 losses.append(train_one_epoch(model, loaders[c], criterion, optimizer, scheduler, scaler,
                                               None, device, config, e + 1, logger))
+            if c == mine[-1]:
+                ev[1].record()  # the aggregate: this rank's last fold (in place) + allreduce + bf16 re-cast
             agg.fold(sizes[c], n_total, client_id=c, last=c == mine[-1])
-        ev[1].record()
+        if not mine:
+            ev[1].record()
         agg.finish(root=root)
         if ema is not None:
             ema.update()  # shadow <- decay * shadow + (1 - decay) * w^{r+1}: identical on every rank
