@@ -486,6 +486,10 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
 int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                      int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
 
+// second-generation backward, keys on lanes (attention_bwd2.cu); FEDVIT_ATTN_BWD=v1 keeps the first kernel
+int attention_tc_bwd2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                      int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
+
 int attention_tc_fwd_long(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
                           float scale, cudaStream_t stream);
 
@@ -554,8 +558,13 @@ extern "C" int fv_attention_bwd(const void* qkv, const void* out, const void* do
   FV_CHECK_ARG(batch > 0 && tokens > 0 && heads > 0 && batch * heads <= 65535 && tokens < (1 << 20),
                "fv_attention_bwd: shape out of range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (use_tc_attention(tokens))
-    return attention_tc_bwd(qkv, out, dout, lse, dqkv, batch, tokens, heads, scale, st);
+  if (use_tc_attention(tokens)) {
+    // FEDVIT_ATTN_BWD=v1: the first-generation (queries on lanes) kernel, for A/B runs (read per call)
+    const char* e = getenv("FEDVIT_ATTN_BWD");
+    const bool v1 = e != nullptr && e[0] == 'v' && e[1] == '1';
+    return v1 ? attention_tc_bwd(qkv, out, dout, lse, dqkv, batch, tokens, heads, scale, st)
+              : attention_tc_bwd2(qkv, out, dout, lse, dqkv, batch, tokens, heads, scale, st);
+  }
   const long long rows = batch * tokens * heads;
   FV_CHECK_CUDA(fv::launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(ceil_div(rows, 8))), dim3(256), 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta,

@@ -239,8 +239,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 }
 
 // 3-D map over qkv [B, N, 3*H*64] bf16: box = 64 columns x `rows` tokens x 1 image
-static int make_qkv_map(CUtensorMap* map, const void* base, int64_t batch, int64_t tokens, int64_t width,
-                        int rows) {
+int make_qkv_map(CUtensorMap* map, const void* base, int64_t batch, int64_t tokens, int64_t width,
+                 int rows) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
