@@ -559,9 +559,12 @@ extern "C" int fv_attention_bwd(const void* qkv, const void* out, const void* do
                "fv_attention_bwd: shape out of range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_tc_attention(tokens)) {
-    // FEDVIT_ATTN_BWD=v1: the first-generation (queries on lanes) kernel, for A/B runs (read per call)
+    // FEDVIT_ATTN_BWD=v2: the keys-on-lanes kernel (attention_bwd2.cu) — numerically equivalent (P enters
+    // dS rounded to bf16: dq / dk error 2.4e-3 -> 2.9e-3 against fp64) and, as measured so far, no faster
+    // than the first-generation kernel (208 vs 212 us at 256 x 197 x 12), which therefore stays the
+    // default; read per call so one process can A/B them
     const char* e = getenv("FEDVIT_ATTN_BWD");
-    const bool v1 = e != nullptr && e[0] == 'v' && e[1] == '1';
+    const bool v1 = !(e != nullptr && e[0] == 'v' && e[1] == '2');
     return v1 ? attention_tc_bwd(qkv, out, dout, lse, dqkv, batch, tokens, heads, scale, st)
               : attention_tc_bwd2(qkv, out, dout, lse, dqkv, batch, tokens, heads, scale, st);
   }

@@ -35,6 +35,16 @@
 // (P = 0) and zero dO rows (dP = delta = 0).
 #include "common.cuh"
 
+// A/B build switches (tools/build_variants.py compiles one library per setting). Measured at
+// (256, 197, 12), profiles/r2_attn_bwd_variants.txt: coalesced helper loads 212 -> 270 us (8 dependent
+// global round trips per item instead of 4), early accumulator release 212 -> 264 us — both off.
+#ifndef B2_HELPER_COALESCED
+#define B2_HELPER_COALESCED 0
+#endif
+#ifndef B2_EARLY_RELEASE
+#define B2_EARLY_RELEASE 0
+#endif
+
 namespace fv {
 
 int make_qkv_map(CUtensorMap* map, const void* base, int64_t batch, int64_t tokens, int64_t width, int rows);
@@ -126,6 +136,11 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   const uint32_t tmem = *tmem_slot;
   pdl_wait();  // nothing above touches memory another kernel produced
   constexpr uint32_t T_X = 0, T_Y = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
+
+  // Registers: 384 threads x 168. The math warps keep P between the phases as the packed bf16 pairs the
+  // tensor core reads (32 registers, unpacked again in phase B); kept as 64 fp32 values ptxas parked them
+  // in local memory and every phase-B multiply waited for an LDL (ncu: 2x slower than the kernel this
+  // replaces). setmaxnreg re-partitioning (104 / 200) made ptxas spill MORE here and is not used.
 
   if (warp == 9) {
     // ------------------------------ TMA producer (whole warp, elected lane issues) ----------------
@@ -307,7 +322,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     // ------------------------------ delta / LSE helpers ------------------------------------------
     // delta[q] * scale = scale * sum_d dO[q,d] * O[q,d] and lse[q] * log2(e) of the NEXT items, straight
     // from global memory (O never occupies shared memory), up to B2_AUX - 1 items ahead of the math warps
-    const int t = threadIdx.x - 320;
     int n = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
       const int b = item / p.H, h = item % p.H;
@@ -315,49 +329,88 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       if (n >= B2_AUX) mbar_wait(&bar_auxfree[slot], (n / B2_AUX - 1) & 1);  // previous tenant read out
       float* aux = sAux + slot * 512;
       const float* lse_bh = p.lse + (static_cast<long long>(b) * p.H + h) * p.N;
-      // two rows per pass: 32 independent 128-bit loads in flight per thread
-      for (int q0 = t; q0 < nt * 128; q0 += 128) {
-        uint4 a[2][8], g[2][8];
-        float l2[2] = {INFINITY, INFINITY};
+#if B2_HELPER_COALESCED
+      // Eight lanes per row: a warp-wide 128-bit load covers four whole 128-byte rows (4 wavefronts of the
+      // L1 data pipe). One row per THREAD, as the first kernel reads them, touches 32 different lines per
+      // instruction — 32 wavefronts — and the two helper warps alone produced half of that pipe's load/store
+      // traffic (ncu: ~1000 of ~2000 LSU wavefronts per cell), on the pipe this kernel is bound by.
+      const int sub = lane & 7, rsel = lane >> 3;  // 16-byte piece of the row, row within the group of 4
+      const int hw = warp - 10;                    // helper warp 0 / 1
+      for (int q0 = hw * 4; q0 < nt * 128; q0 += 8 * 4) {
+        // 4 passes of 4 rows per iteration: 8 independent 128-bit loads in flight per thread
+        float acc[4];
+        uint4 a[4], g[4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int q = q0 + j * 64;
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * 8 + rsel;
           if (q < p.N) {
             const long long off = (static_cast<long long>(b) * p.N + q) * hd + h * 64;
-            const uint4* orow = reinterpret_cast<const uint4*>(p.o + off);
-            const uint4* grow = reinterpret_cast<const uint4*>(p.dout + off);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              a[j][u] = __ldg(orow + u);
-              g[j][u] = __ldg(grow + u);
-            }
-            l2[j] = __ldg(lse_bh + q) * B2_LOG2E;
+            a[u] = __ldg(reinterpret_cast<const uint4*>(p.o + off) + sub);
+            g[u] = __ldg(reinterpret_cast<const uint4*>(p.dout + off) + sub);
           } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[j][u] = g[j][u] = make_uint4(0u, 0u, 0u, 0u);
+            a[u] = g[u] = make_uint4(0u, 0u, 0u, 0u);
           }
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int q = q0 + j * 64;
-          float acc = 0.f;
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+          const uint32_t gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+          float t = 0.f;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const uint32_t aw[4] = {a[j][u].x, a[j][u].y, a[j][u].z, a[j][u].w};
-            const uint32_t gw[4] = {g[j][u].x, g[j][u].y, g[j][u].z, g[j][u].w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const float2 af = unpack_bf16(aw[w]), gf = unpack_bf16(gw[w]);
-              acc = fmaf(af.x, gf.x, acc);
-              acc = fmaf(af.y, gf.y, acc);
-            }
+          for (int w = 0; w < 4; ++w) {
+            const float2 af = unpack_bf16(aw[w]), gf = unpack_bf16(gw[w]);
+            t = fmaf(af.x, gf.x, t);
+            t = fmaf(af.y, gf.y, t);
           }
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          t += __shfl_xor_sync(0xffffffffu, t, 4);
+          acc[u] = t;
+        }
+        if (sub < 4) {  // lane `sub` of each group of eight publishes row u = sub
+          const int q = q0 + sub * 8 + rsel;
+          const float t = sub == 0 ? acc[0] : sub == 1 ? acc[1] : sub == 2 ? acc[2] : acc[3];
           if (q < nt * 128) {
-            aux[q] = l2[j];
-            aux[256 + q] = acc * p.scale;
+            aux[q] = q < p.N ? __ldg(lse_bh + q) * B2_LOG2E : INFINITY;
+            aux[256 + q] = t * p.scale;
           }
         }
       }
+#else
+      // one row per thread and pass, 16 independent 128-bit loads in flight per thread
+      for (int q = threadIdx.x - 320; q < nt * 128; q += 64) {
+        uint4 a[8], g[8];
+        float l2 = INFINITY;
+        if (q < p.N) {
+          const long long off = (static_cast<long long>(b) * p.N + q) * hd + h * 64;
+          const uint4* orow = reinterpret_cast<const uint4*>(p.o + off);
+          const uint4* grow = reinterpret_cast<const uint4*>(p.dout + off);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            a[u] = __ldg(orow + u);
+            g[u] = __ldg(grow + u);
+          }
+          l2 = __ldg(lse_bh + q) * B2_LOG2E;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) a[u] = g[u] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+          const uint32_t gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 af = unpack_bf16(aw[w]), gf = unpack_bf16(gw[w]);
+            acc = fmaf(af.x, gf.x, acc);
+            acc = fmaf(af.y, gf.y, acc);
+          }
+        }
+        aux[q] = l2;
+        aux[256 + q] = acc * p.scale;
+      }
+#endif
       mbar_arrive(&bar_aux[slot]);
     }
   } else if (warp < 8) {
@@ -375,11 +428,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     // 128B-swizzle layout. The 3-D tensor map clips rows past the sequence end.
     uint8_t* stage = sStage + warp * B2_STAGE;
     bool store_pending = false;
-    auto store_row = [&](uint32_t col, int b, int h, int slot, int tile) {
-      // two passes of 32 columns: the accumulator row is packed to bf16 as it arrives, so only 32 + 32
-      // registers are live on top of the caller's (the drain runs between the two phases of a cell)
-      uint32_t w[32];
-      const int tok0 = tile * 128 + quarter * 32;  // first row of this warp
+    // part 1: the accumulator row leaves tensor memory (packed to bf16 as it arrives: two passes of 32
+    // columns) — after this the MMA warp may overwrite the accumulator
+    auto load_row = [&](uint32_t col, uint32_t (&w)[32]) {
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
         uint32_t o[32];
@@ -389,6 +440,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         for (int i = 0; i < 16; ++i)
           w[16 * part + i] = pack_bf16(__uint_as_float(o[2 * i]), __uint_as_float(o[2 * i + 1]));
       }
+    };
+    // part 2: staging tile -> TMA tensor store, 16 rows at a time
+    auto store_row = [&](const uint32_t (&w)[32], int b, int h, int slot, int tile) {
+      const int tok0 = tile * 128 + quarter * 32;  // first row of this warp
       if (tok0 >= p.N) return;  // warp-uniform
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -422,16 +477,34 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       if (!(pend_kv || pend_dq)) return;
       mbar_wait(&bar_m2[pend_it & 1], (pend_it >> 1) & 1);  // the cell that completed them has retired
       tc_fence_after();
+      // the accumulators are released the moment they are in registers: the MMA warp's next dV (which
+      // overwrites them) does not wait for the staging stores and the TMA issue
       if (pend_kv) {
-        store_row(hf == 0 ? T_DK : T_DV, kv_b, kv_h, hf == 0 ? 1 : 2, kv_kb);
+        uint32_t w[32];
+        load_row(hf == 0 ? T_DK : T_DV, w);
+#if B2_EARLY_RELEASE
         tc_fence_before();
         mbar_arrive(bar_kvfree);
+        store_row(w, kv_b, kv_h, hf == 0 ? 1 : 2, kv_kb);
+#else
+        store_row(w, kv_b, kv_h, hf == 0 ? 1 : 2, kv_kb);
+        tc_fence_before();
+        mbar_arrive(bar_kvfree);
+#endif
         pend_kv = false;
       }
       if (pend_dq) {
-        if (hf < nt) store_row(T_DQ + hf * 64, dq_b, dq_h, 0, hf);
+        uint32_t w[32];
+        if (hf < nt) load_row(T_DQ + hf * 64, w);
+#if B2_EARLY_RELEASE
         tc_fence_before();
         mbar_arrive(bar_dqfree);
+        if (hf < nt) store_row(w, dq_b, dq_h, 0, hf);
+#else
+        if (hf < nt) store_row(w, dq_b, dq_h, 0, hf);
+        tc_fence_before();
+        mbar_arrive(bar_dqfree);
+#endif
         pend_dq = false;
       }
     };
@@ -450,41 +523,35 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #pragma unroll
           for (int c = 0; c < 2; ++c) valid[c] = rows_live && (32 * (2 * c + hf) < nq);  // warp-uniform
           // ================= phase A: P^T = exp2(S^T * scale*log2e - lse*log2e), written over S^T =========
-          float pr[2][32];
+          // P is kept as the packed bf16 pairs the tensor core reads (16 registers per chunk) — phase B
+          // unpacks them again (a shift / a mask per value): 32 instead of 64 registers live across the drain
+          uint32_t pk[2][16];
           mbar_wait(bar_sx, it & 1);
           tc_fence_after();
-          {
-            uint32_t s0[32], s1[32];
-            if (valid[0]) tmem_ld_32x32(lane_base + T_X + 32 * hf, s0);
-            if (valid[1]) tmem_ld_32x32(lane_base + T_X + 32 * (2 + hf), s1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              if (valid[c]) {
-                const uint32_t* s = c == 0 ? s0 : s1;
-                const float4* l2v = reinterpret_cast<const float4*>(aux + qt * 128 + 32 * (2 * c + hf));
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 l2 = l2v[i >> 2];
-                  pr[c][i] = b2_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2.x));
-                  pr[c][i + 1] = b2_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2.y));
-                  pr[c][i + 2] = b2_ex2(fmaf(__uint_as_float(s[i + 2]), sl2, -l2.z));
-                  pr[c][i + 3] = b2_ex2(fmaf(__uint_as_float(s[i + 3]), sl2, -l2.w));
-                }
-              }
-            }
-          }
-          // every S^T value of both chunks is in registers before any P^T column is written: chunk j's
-          // 16 packed columns land inside chunk j's own 32 score columns, which only this thread reads
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             if (valid[c]) {
-              uint32_t pk[16];
+              uint32_t s[32];
+              tmem_ld_32x32(lane_base + T_X + 32 * (2 * c + hf), s);
+              tmem_ld_wait();
+              const float4* l2v = reinterpret_cast<const float4*>(aux + qt * 128 + 32 * (2 * c + hf));
 #pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pr[c][2 * i], pr[c][2 * i + 1]);
-              tmem_st_32x16(lane_base + T_X + 32 * (2 * c + hf), pk);
+              for (int i = 0; i < 32; i += 4) {
+                const float4 l2 = l2v[i >> 2];
+                const float p0 = b2_ex2(fmaf(__uint_as_float(s[i]), sl2, -l2.x));
+                const float p1 = b2_ex2(fmaf(__uint_as_float(s[i + 1]), sl2, -l2.y));
+                const float p2 = b2_ex2(fmaf(__uint_as_float(s[i + 2]), sl2, -l2.z));
+                const float p3 = b2_ex2(fmaf(__uint_as_float(s[i + 3]), sl2, -l2.w));
+                pk[c][i >> 1] = pack_bf16(p0, p1);
+                pk[c][(i >> 1) + 1] = pack_bf16(p2, p3);
+              }
             }
           }
+          // chunk j's 16 packed columns land inside chunk j's own 32 score columns, which only this thread
+          // reads — and has read: both chunks are in registers before the first P^T column is written
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (valid[c]) tmem_st_32x16(lane_base + T_X + 32 * (2 * c + hf), pk[c]);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_pt);
@@ -516,10 +583,11 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 dl = dlv[i >> 2];
-                const float s0 = pr[c][i] * fmaf(__uint_as_float(d[i]), p.scale, -dl.x);
-                const float s1 = pr[c][i + 1] * fmaf(__uint_as_float(d[i + 1]), p.scale, -dl.y);
-                const float s2 = pr[c][i + 2] * fmaf(__uint_as_float(d[i + 2]), p.scale, -dl.z);
-                const float s3 = pr[c][i + 3] * fmaf(__uint_as_float(d[i + 3]), p.scale, -dl.w);
+                const float2 pa = unpack_bf16(pk[c][i >> 1]), pb = unpack_bf16(pk[c][(i >> 1) + 1]);
+                const float s0 = pa.x * fmaf(__uint_as_float(d[i]), p.scale, -dl.x);
+                const float s1 = pa.y * fmaf(__uint_as_float(d[i + 1]), p.scale, -dl.y);
+                const float s2 = pb.x * fmaf(__uint_as_float(d[i + 2]), p.scale, -dl.z);
+                const float s3 = pb.y * fmaf(__uint_as_float(d[i + 3]), p.scale, -dl.w);
                 dk[i >> 1] = pack_bf16(s0, s1);
                 dk[(i >> 1) + 1] = pack_bf16(s2, s3);
               }

@@ -13,7 +13,7 @@ our own GEMMs, so a training step launches no library GEMM at all:
 
 Parameter gradients are accumulated straight into ``p.grad`` (the FlatArena buffer when there is
 one), like the backbone's. Dropout uses torch's RNG for the mask (plumbing) and folds it into the
-saved GELU'. The 13-d metadata MLP (BatchNorm1d) stays on stock PyTorch ops.
+saved GELU'. The 13-d metadata MLP (BatchNorm1d) has its own fused kernels: ``metadata.py``.
 """
 from __future__ import annotations
 

@@ -8,8 +8,8 @@ the backbone is ``fedvit_b200.vit.VisionTransformer`` (hand-written sm_100a kern
 backward) instead of a timm module running on ATen/cuDNN/cuBLAS.
 
 Scope notes: only the ViT family is on this path — the reference's default
-SwinV2 backbone name raises. The classifier head runs on the libfedvit GEMMs (``head.py``, row f2
-of the scope table); the 13-d metadata MLP (BatchNorm1d) stays on stock PyTorch ops.
+SwinV2 backbone name raises. The classifier head (``head.py``) and the 13-d metadata MLP incl. its
+BatchNorm1d (``metadata.py``) run on libfedvit kernels as well (row f2 of the scope table).
 """
 from __future__ import annotations
 
@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from . import timm_b200 as timm
 from .head import classifier_head
+from .metadata import metadata_embedding
 
 _DEFAULT_BACKBONE = "swinv2_large_window12to24_192to384.ms_in22k_ft_in1k"  # reference model.py:89
 
@@ -39,7 +40,9 @@ class MetadataBranch(nn.Module):
         self.net = nn.Sequential(*stages)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.net(x)
+        # the Sequential's modules hold the parameters / running statistics (reference state_dict keys
+        # metadata_branch.net.{0,1,4,5}.*); the arithmetic is two fused kernels (metadata.py)
+        return metadata_embedding(x, self.net, self.training)
 
 
 class ISICClassifier(nn.Module):

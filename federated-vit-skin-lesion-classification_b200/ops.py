@@ -435,6 +435,72 @@ def colsum(a: Tensor, out: Tensor, accumulate: bool) -> None:
 
 
 # ------------------------------------------------------------------------------------------------
+# metadata branch stage: Linear + BatchNorm1d + GELU (+ dropout mask), scope row f2
+# ------------------------------------------------------------------------------------------------
+@_op("fedvit::linear_bn_gelu_fwd", mutates_args=("running_mean", "running_var", "y"))
+def linear_bn_gelu_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], gamma: Tensor, beta: Tensor,
+                       running_mean: Tensor, running_var: Tensor, momentum: float, eps: float, training: bool,
+                       drop_mask: Optional[Tensor], y: Tensor, save: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """y = drop_mask * gelu(batchnorm(x w^T + bias)) — one stage of reference model.py:27-60. ``y`` may be
+    a column slice of a wider row-major buffer. Returns (xhat, dact, rstd) for the backward (``dact``
+    empty unless ``save``); the running statistics are updated in place when ``training``."""
+    _need_cuda(x, w, bias, gamma, beta, running_mean, running_var, drop_mask, y)
+    if x.dim() != 2 or w.dim() != 2 or x.shape[1] != w.shape[1] or x.stride(1) != 1 or not w.is_contiguous():
+        raise FedVitError("linear_bn_gelu_fwd: x [B, in] row-major, w [out, in] contiguous")
+    b, k = x.shape
+    f = w.shape[0]
+    for t in (x, w, gamma, beta, running_mean, running_var, y):
+        if t.dtype != torch.float32:
+            raise FedVitError("linear_bn_gelu_fwd: fp32 tensors required")
+    if tuple(y.shape) != (b, f) or y.stride(1) != 1:
+        raise FedVitError("linear_bn_gelu_fwd: y must be [B, out] with unit inner stride")
+    if drop_mask is not None and (tuple(drop_mask.shape) != (b, f) or not drop_mask.is_contiguous()
+                                  or drop_mask.dtype != torch.float32):
+        raise FedVitError("linear_bn_gelu_fwd: drop_mask must be contiguous fp32 [B, out]")
+    if training and b < 2:
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")
+    xhat = torch.empty((b, f), device=x.device, dtype=torch.float32)
+    dact = torch.empty((b, f) if save else (0,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((f,), device=x.device, dtype=torch.float32)
+    LIB.call("fv_linear_bn_gelu_fwd", x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(bias), gamma.data_ptr(),
+             beta.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(), momentum, eps, int(training),
+             _ptr(drop_mask), y.data_ptr(), y.stride(0), xhat.data_ptr(), dact.data_ptr() if save else None,
+             rstd.data_ptr(), b, k, f, _stream(x))
+    return xhat, dact, rstd
+
+
+@linear_bn_gelu_fwd.register_fake
+def _(x, w, bias, gamma, beta, running_mean, running_var, momentum, eps, training, drop_mask, y, save):
+    b, f = x.shape[0], w.shape[0]
+    return x.new_empty((b, f)), x.new_empty((b, f) if save else (0,)), x.new_empty((f,))
+
+
+@_op("fedvit::linear_bn_gelu_bwd", mutates_args=("dw", "dbias", "dgamma", "dbeta"))
+def linear_bn_gelu_bwd(dy: Tensor, x: Tensor, xhat: Tensor, dact: Tensor, rstd: Tensor, gamma: Tensor,
+                       training: bool, dw: Optional[Tensor], dbias: Optional[Tensor], dgamma: Optional[Tensor],
+                       dbeta: Optional[Tensor]) -> Tensor:
+    """Backward of ``linear_bn_gelu_fwd``: returns dh [B, out] (gradient w.r.t. the Linear output) and
+    accumulates dw / dbias / dgamma / dbeta in place."""
+    _need_cuda(dy, x, xhat, dact, rstd, gamma, dw, dbias, dgamma, dbeta)
+    b, f = xhat.shape
+    k = x.shape[1]
+    if dy.dtype != torch.float32 or tuple(dy.shape) != (b, f) or dy.stride(1) != 1 or x.stride(1) != 1:
+        raise FedVitError("linear_bn_gelu_bwd: dy [B, out] fp32 with unit inner stride")
+    if dw is not None and (tuple(dw.shape) != (f, k) or not dw.is_contiguous()):
+        raise FedVitError("linear_bn_gelu_bwd: dw must be contiguous [out, in]")
+    dh = torch.empty((b, f), device=dy.device, dtype=torch.float32)
+    LIB.call("fv_linear_bn_gelu_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), xhat.data_ptr(),
+             dact.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), int(training), dh.data_ptr(), _ptr(dw), _ptr(dbias),
+             _ptr(dgamma), _ptr(dbeta), b, k, f, _stream(dy))
+    return dh
+
+
+@linear_bn_gelu_bwd.register_fake
+def _(dy, x, xhat, dact, rstd, gamma, training, dw, dbias, dgamma, dbeta):
+    return dy.new_empty(xhat.shape)
+
+
+# ------------------------------------------------------------------------------------------------
 # losses
 # ------------------------------------------------------------------------------------------------
 @_op("fedvit::asl_loss", mutates_args=())

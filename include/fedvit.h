@@ -274,6 +274,32 @@ int fv_fedavg_accum(float* acc, const float* w, float weight, int init, int64_t 
 int fv_fedavg_fold_into(const float* acc, const float* w, float weight, float* out, void* out_lp,
                         int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One stage of the reference's MetadataBranch (model.py:27-60), fused:
+ *     y = dropout_mask * GELU_erf(BatchNorm1d(x W^T + b))
+ * Replaces nn.Linear + nn.BatchNorm1d (training: batch statistics over the batch dimension, biased
+ * variance for the normalisation, running_mean / running_var updated with momentum and the UNBIASED
+ * variance; eval: running statistics) + nn.GELU + nn.Dropout's multiply (scope row f2; the metadata
+ * branch is enabled in the reference's default config.yaml:34-40). fp32.
+ *   x [batch, in] (ldx), w [out, in], bias / gamma / beta [out], running_* [out] (updated in place when
+ *   training), drop_mask [batch, out] (keep / keep_prob, or NULL)
+ *   y [batch, out] (ldy: may be a column slice of a wider buffer)
+ *   saved for the backward: xhat [batch, out] (normalised pre-affine values), dact [batch, out]
+ *   (= drop_mask * GELU'(z); may be NULL in inference), rstd [out] (may be NULL)
+ * Backward: dh [batch, out] (gradient w.r.t. the Linear output; the caller multiplies it by W for dx),
+ *   and ACCUMULATES (+=) dw [out, in], dbias, dgamma, dbeta (each may be NULL).
+ * One CTA owns 8 features for all rows, so every batch reduction stays inside a CTA: no atomics,
+ * bit-reproducible.
+ * ---------------------------------------------------------------------------------------- */
+int fv_linear_bn_gelu_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                          int training, const float* drop_mask, float* y, int64_t ldy, float* xhat, float* dact,
+                          float* rstd, int64_t batch, int64_t in_features, int64_t out_features, void* stream);
+int fv_linear_bn_gelu_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* xhat,
+                          const float* dact, const float* rstd, const float* gamma, int training, float* dh,
+                          float* dw, float* dbias, float* dgamma, float* dbeta, int64_t batch,
+                          int64_t in_features, int64_t out_features, void* stream);
+
 /* fp32 attention helpers for the parity path: row softmax fwd/bwd on [rows, cols] scores      */
 int fv_softmax_rows(const float* s, float* p, int64_t rows, int64_t cols, float scale, void* stream);
 int fv_softmax_rows_bwd(const float* p, const float* dp, float* ds, int64_t rows, int64_t cols,

@@ -46,8 +46,9 @@ def check(B, N, H, seed=0):
         os.environ["FEDVIT_ATTN_BWD"] = ver
         d = ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).float().view(B * N, 3, H * 64)
         torch.cuda.synchronize()
+        floor = 1e-3 * (float(ref.norm()) + 1e-6 * float(dout.double().norm()))  # N == 1: dq, dk are exactly 0
         for i, name in enumerate("qkv"):
-            den = max(float(ref[:, i].norm()), 1e-9)
+            den = max(float(ref[:, i].norm()), floor)
             res[f"{ver}.d{name}"] = float((d[:, i].double().cpu() - ref[:, i].cpu()).norm()) / den
         again = ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).float().view(B * N, 3, H * 64)
         res[f"{ver}.repro"] = bool(torch.equal(again, d))
@@ -79,6 +80,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--skip-check", action="store_true")
+    ap.add_argument("--one", action="store_true", help="time the benchmark shape only (ncu captures)")
     args = ap.parse_args()
     ok = True
     if not args.skip_check:
@@ -86,7 +88,7 @@ def main():
                       (40, 197, 12), (300, 197, 3)]:
             ok &= check(*shape)
     scale = 0.125
-    for (B, N, H) in [(256, 197, 12), (64, 197, 12), (1024, 197, 3)]:
+    for (B, N, H) in ([(256, 197, 12)] if args.one else [(256, 197, 12), (64, 197, 12), (1024, 197, 3)]):
         g = torch.Generator(device=DEV).manual_seed(1)
         qkv = torch.randn(B * N, 3 * H * 64, device=DEV, generator=g).bfloat16()
         dout = torch.randn(B * N, H * 64, device=DEV, generator=g).bfloat16()
