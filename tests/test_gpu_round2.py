@@ -406,3 +406,122 @@ def test_asl_gradient_edge_cases_match_autograd_conventions():
     assert torch.isnan(bad)
     bad, _ = ops.ce_loss(logits, torch.tensor([-1, 1], device=DEV))
     assert torch.isnan(bad)
+
+
+# ------------------------------------------------------------------------------------------------
+# native metadata branch (scope row f2): Linear + BatchNorm1d + GELU (+ dropout) fused stages
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [2, 37, 256])
+def test_metadata_branch_kernels_match_torch_modules(batch):
+    """``MetadataBranch`` on the fused kernels against the same Sequential run by stock nn modules (the
+    reference's model.py:27-60 arithmetic): embedding, every parameter gradient, running statistics and
+    num_batches_tracked, in training mode (batch statistics) and eval mode (running statistics)."""
+    from fedvit_b200.model import MetadataBranch
+
+    torch.manual_seed(batch)
+    ours = MetadataBranch(13, 256, 128, dropout=0.0).to(DEV)
+    ref = torch.nn.Sequential(
+        torch.nn.Linear(13, 256), torch.nn.BatchNorm1d(256), torch.nn.GELU(), torch.nn.Dropout(0.0),
+        torch.nn.Linear(256, 128), torch.nn.BatchNorm1d(128), torch.nn.GELU()).to(DEV)
+    with torch.no_grad():
+        for p in ours.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.1)
+    ref.load_state_dict(ours.net.state_dict())
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for step_i in range(3):  # running statistics accumulate over steps
+        x = torch.rand(batch, 13, device=DEV, generator=g)
+        dy = torch.randn(batch, 128, device=DEV, generator=g)
+        ours.train(), ref.train()
+        ours.zero_grad(set_to_none=True), ref.zero_grad(set_to_none=True)
+        a = ours(x)
+        a.backward(dy)
+        b = ref(x)
+        b.backward(dy)
+        assert rel_err(a, b) < 1e-5
+        grads = dict(ours.net.named_parameters())
+        for (n, p), (_, q) in zip(ours.net.named_parameters(), ref.named_parameters()):
+            if n in ("0.bias", "4.bias"):
+                # a bias in front of a training-mode BatchNorm has a mathematically zero gradient (the batch
+                # mean absorbs it): both sides hold rounding noise only
+                wmax = float(grads[n.replace("bias", "weight")].grad.abs().max())
+                assert float(p.grad.abs().max()) < 1e-3 * wmax and float(q.grad.abs().max()) < 1e-3 * wmax, (step_i, n)
+                continue
+            assert rel_err(p.grad, q.grad) < 2e-4, (step_i, n)
+        for (n, u), (_, v) in zip(ours.net.named_buffers(), ref.named_buffers()):
+            if u.is_floating_point():
+                assert rel_err(u, v) < 1e-5, (step_i, n)
+            else:
+                assert int(u) == int(v) == step_i + 1, n
+    ours.eval(), ref.eval()
+    x = torch.rand(batch, 13, device=DEV, generator=g)
+    with torch.no_grad():
+        assert rel_err(ours(x), ref(x)) < 1e-5
+    xg = x.clone()
+    ours.zero_grad(set_to_none=True), ref.zero_grad(set_to_none=True)
+    ours(xg).sum().backward()   # eval-mode backward: running statistics, no batch correction terms
+    ref(xg).sum().backward()
+    for (n, p), (_, q) in zip(ours.net.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad, q.grad) < 2e-4, n
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        ours(x)
+    assert _lib.launch_count() - n0 == 2  # the whole branch is two launches
+
+
+def test_metadata_branch_dropout_and_errors():
+    from fedvit_b200.model import MetadataBranch
+
+    torch.manual_seed(0)
+    m = MetadataBranch(13, 64, 32, dropout=0.5).to(DEV).train()
+    x = torch.rand(64, 13, device=DEV)
+    torch.manual_seed(5)
+    a = m(x)
+    torch.manual_seed(5)
+    b = m(x)
+    assert torch.equal(a, b)               # the mask comes from torch's generator: reproducible under a seed
+    m.eval()
+    with torch.no_grad():
+        c = m(x)
+    assert not torch.equal(a, c)
+    m.train()
+    with pytest.raises(ValueError):
+        m(x[:1])                            # BatchNorm1d: more than one value per channel in training mode
+    with pytest.raises(Exception):
+        m(x.cpu())
+
+
+def test_fedavg_round_with_metadata_branch_averages_running_stats_vs_oracle(golden_rgb):
+    """``metadata.enabled: true`` (the reference default) through a whole FedAvg round on the GPU path:
+    parameters AND BatchNorm running statistics are sample-weighted averages, num_batches_tracked comes
+    from client 0 — against the oracle doing the same on CPU."""
+    cfg = micro_config()
+    cfg["model"]["metadata"] = {"enabled": True, "input_dim": 13, "hidden_dim": 32, "output_dim": 16, "dropout": 0.0}
+    cfg["training"]["optimizer"] = {"lr": 2e-5, "weight_decay": 1e-2}
+    sizes = [24, 12]
+    cfg["federated"] = {"num_clients": 2, "rounds": 1, "local_epochs": 1, "samples_per_client": sizes}
+    out = train.run_federated(cfg, device=DEV)
+    ours = out["model"]
+    utils.seed_everything(42)
+    init = model.build_model(cfg).state_dict()
+    finals = []
+    for c in range(2):
+        ora = isic.model_from_config(cfg)
+        ora.load_state_dict(init)
+        loader = data.SyntheticClientLoader(c, sizes[c], 6, 32, num_classes=7, metadata_dim=13, pin=False)
+        oopt = torch.optim.AdamW(isic.llrd_groups(ora, 2e-5, 0.75, 1e-2), weight_decay=1e-2)
+        step.local_epoch(ora, list(loader), asl.loss_from_config(cfg), oopt, grad_clip=1.0, use_meta=True)
+        finals.append({k: v.clone() for k, v in ora.state_dict().items()})
+    want = ofed.fedavg_state_dicts(finals, sizes)
+    sd = ours.state_dict()
+    for k in ("metadata_branch.net.1.running_mean", "metadata_branch.net.1.running_var",
+              "metadata_branch.net.5.running_mean", "metadata_branch.net.5.running_var"):
+        assert rel_err(sd[k], want[k]) < 1e-3, k
+        assert not torch.allclose(sd[k].cpu(), init[k])  # they moved, and were averaged
+    for k in ("metadata_branch.net.1.num_batches_tracked", "metadata_branch.net.5.num_batches_tracked"):
+        assert int(sd[k]) == int(want[k]) == 4  # client 0's count: 24 samples / batch 6
+    upd = max(float((want[k].double() - init[k].double()).norm()) for k in want if want[k].is_floating_point())
+    for k, v in sd.items():
+        if v.is_floating_point():
+            err = float((v.detach().double().cpu() - want[k].double()).norm())
+            assert err < 1e-2 * max(float(want[k].double().norm()), upd), k
