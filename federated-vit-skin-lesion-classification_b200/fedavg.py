@@ -39,16 +39,19 @@ def dist_info():
     return 0, 1
 
 
-def assign_clients(sizes: Sequence[int], world: int) -> List[List[int]]:
+def assign_clients(sizes: Sequence[int], world: int, policy: str = "auto") -> List[List[int]]:
     """Clients of every rank. Equal shard sizes: client k -> rank k mod G. Unequal
     sizes: longest-processing-time-first — clients in descending n_k (ties: lower id first), each to
     the rank with the least samples so far (ties: lowest rank) — because the round ends when the most
     loaded GPU does. Deterministic, identical on every rank; within a rank clients run and are
-    folded in ascending id, so the single-GPU fold order (and its bit-exactness) is unchanged."""
+    folded in ascending id, so the single-GPU fold order (and its bit-exactness) is unchanged.
+    ``policy`` (config key ``federated.placement``): "auto" (the above), "lpt", or "round_robin"."""
     k = len(sizes)
+    if policy not in ("auto", "lpt", "round_robin"):
+        raise ValueError(f"unknown federated.placement {policy!r} (auto | lpt | round_robin)")
     if world <= 1:
         return [list(range(k))]
-    if len(set(int(s) for s in sizes)) <= 1:
+    if policy == "round_robin" or (policy == "auto" and len(set(int(s) for s in sizes)) <= 1):
         return [[c for c in range(k) if c % world == r] for r in range(world)]
     load = [0] * world
     out: List[List[int]] = [[] for _ in range(world)]

@@ -379,7 +379,7 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
 
     sizes = client_sizes(config)
     n_total = sum(sizes)
-    placement = assign_clients(sizes, world)
+    placement = assign_clients(sizes, world, str(fed.get("placement", "auto")))
     mine = placement[rank]
     root = next(r for r, cs in enumerate(placement) if 0 in cs)  # integer buffers come from client 0
     if loaders is None:
