@@ -430,6 +430,7 @@ def run_gpu_arm(args) -> None:
     round_info = {
         "round_ms": round_ms, "round_ms_all": [r["round_ms"] for r in rounds], "warmup_rounds": 1,
         "aggregate_ms_in_round": min(r["aggregate_ms"] for r in timed),
+        "aggregate_ms_in_round_last_rank": min(r["aggregate_ms_last_rank"] for r in timed),
         "round_images_per_s": args.gpus * n_k / (round_ms / 1e3),
         "steps_x_ms_step": STEPS_PER_ROUND * ms_step,
         "gap_to_steps_ms": round_ms - STEPS_PER_ROUND * ms_step,
@@ -463,7 +464,8 @@ def run_gpu_arm(args) -> None:
             "workload": f"ViT-Large/16 384px bf16, {k4} non-IID (Dirichlet 0.5) clients over {args.gpus} GPU(s), "
                         "unequal n_k, sample-weighted FedAvg; round 2 of 2 (shards scaled down 4x from 512...2048)",
             "samples_per_client": sizes4, "placement": place, "samples_per_rank": loads,
-            "round_ms": r4["round_ms"], "aggregate_ms": r4["aggregate_ms"], "rank_busy_ms": busy,
+            "round_ms": r4["round_ms"], "aggregate_ms": r4["aggregate_ms"],
+            "aggregate_ms_last_rank": r4["aggregate_ms_last_rank"], "rank_busy_ms": busy,
             "images_per_s": r4["images_per_s"],
             "imbalance_max_over_mean_busy": max(busy) / (sum(busy) / len(busy)),
             "round_ms_over_balanced_ideal": r4["round_ms"] / (sum(loads) / args.gpus / rate * 1e3),

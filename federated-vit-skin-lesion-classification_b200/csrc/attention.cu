@@ -486,6 +486,10 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int64_t batch, int6
 int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                      int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
 
+// second-generation forward, two threads per query row (attention_fwd2.cu); FEDVIT_ATTN_FWD=v1 keeps the first
+int attention_tc_fwd2(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
+                      float scale, cudaStream_t stream);
+
 // second-generation backward, keys on lanes (attention_bwd2.cu); FEDVIT_ATTN_BWD=v1 keeps the first kernel
 int attention_tc_bwd2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                       int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
@@ -530,8 +534,12 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
                "fv_attention_fwd: shape out of range");
   FV_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "fv_attention_fwd: pointers must be 16-byte aligned");
-  if (use_tc_attention(tokens))
-    return attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
+  if (use_tc_attention(tokens)) {
+    const char* e = getenv("FEDVIT_ATTN_FWD");  // v1 = one thread per query row (first generation); read per call
+    const bool v1 = e != nullptr && e[0] == 'v' && e[1] == '1';
+    return v1 ? attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream))
+              : attention_tc_fwd2(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
+  }
   if (use_tc_attention_long(tokens))
     return attention_tc_fwd_long(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
   dim3 grid(static_cast<unsigned>(ceil_div(tokens, AT_T)), static_cast<unsigned>(batch * heads));

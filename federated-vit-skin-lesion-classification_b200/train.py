@@ -418,8 +418,10 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
         scheduler.step()
         ms = torch.tensor([ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[2])], device=device)
         busy = torch.tensor([ev[0].elapsed_time(ev[1])], device=device)  # this rank's local training + folds
+        agg_min = torch.tensor([ev[1].elapsed_time(ev[2])], device=device)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(agg_min, op=dist.ReduceOp.MIN)
             all_busy = [torch.zeros_like(busy) for _ in range(world)]
             dist.all_gather(all_busy, busy)
             busy = torch.cat(all_busy)
@@ -429,7 +431,11 @@ def run_federated(config: dict, device: Optional[torch.device] = None, logger: O
                            float(sum(sizes[c] for c in mine))], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(lw)
+        # aggregate_ms is the MAX over ranks of (own last fold -> w^{r+1} installed): on every rank but the last
+        # to arrive it includes the wait for the slowest client; aggregate_ms_last_rank (the MIN) is what the
+        # fold + allreduce + re-cast cost once everybody is there
         rec = {"round": rnd, "round_ms": float(ms[0]), "aggregate_ms": float(ms[1]),
+               "aggregate_ms_last_rank": float(agg_min[0]),
                "images_per_s": images / (float(ms[0]) / 1e3),
                "mean_client_loss": float(lw[0] / lw[1]) if float(lw[1]) > 0 else None,
                "rank_busy_ms": [float(v) for v in busy.tolist()]}

@@ -40,8 +40,13 @@ def check(B, N, H, seed=0):
     dout = torch.randn(B * N, H * 64, device=DEV, generator=g).bfloat16()
     scale = 1.0 / math.sqrt(64)
     o, lse_ref, ref = reference(qkv, dout, B, N, H, scale)
+    os.environ["FEDVIT_ATTN_FWD"] = "v1"
+    out1, lse1 = ops.attention_fwd(qkv, B, N, H, scale)
+    os.environ["FEDVIT_ATTN_FWD"] = "v2"
     out, lse = ops.attention_fwd(qkv, B, N, H, scale)
-    res = {"fwd": rel(out, o), "lse": rel(lse, lse_ref)}
+    out_again, _ = ops.attention_fwd(qkv, B, N, H, scale)
+    res = {"fwd1": rel(out1, o), "lse1": rel(lse1, lse_ref), "fwd": rel(out, o), "lse": rel(lse, lse_ref),
+           "fwd.repro": bool(torch.equal(out, out_again))}
     for ver in ("v2", "v1"):
         os.environ["FEDVIT_ATTN_BWD"] = ver
         d = ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale).float().view(B * N, 3, H * 64)
@@ -93,14 +98,16 @@ def main():
         qkv = torch.randn(B * N, 3 * H * 64, device=DEV, generator=g).bfloat16()
         dout = torch.randn(B * N, H * 64, device=DEV, generator=g).bfloat16()
         out, lse = ops.attention_fwd(qkv, B, N, H, scale)
-        t_f = timeit(lambda: ops.attention_fwd(qkv, B, N, H, scale), args.iters)
-        line = f"B={B} N={N} H={H}: fwd {t_f:.1f} us"
         fl = 4.0 * N * N * 64 * B * H
-        line += f" ({fl / t_f / 1e6:.0f} TF/s)"
+        line = f"B={B} N={N} H={H}:"
+        for ver in ("v1", "v2"):
+            os.environ["FEDVIT_ATTN_FWD"] = ver
+            t_f = timeit(lambda: ops.attention_fwd(qkv, B, N, H, scale), args.iters)
+            line += f" fwd {ver} {t_f:.1f} us ({fl / t_f / 1e6:.0f} TF/s) |"
         for ver in ("v1", "v2"):
             os.environ["FEDVIT_ATTN_BWD"] = ver
             t = timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale), args.iters)
-            line += f" | bwd {ver} {t:.1f} us ({2.5 * fl / t / 1e6:.0f} TF/s)"
+            line += f" bwd {ver} {t:.1f} us ({2.5 * fl / t / 1e6:.0f} TF/s) |"
         print(line, flush=True)
     os.environ["FEDVIT_ATTN_BWD"] = "v2"
     print("PARITY", "OK" if ok else "FAILED", flush=True)

@@ -55,7 +55,8 @@ def main():
         rate = sum(loads) / (sum(busy) / 1e3)  # images per busy GPU-second
         out[policy] = {
             "placement": place, "samples_per_rank": loads, "rank_busy_ms": busy, "round_ms": r["round_ms"],
-            "aggregate_ms": r["aggregate_ms"], "images_per_s": r["images_per_s"],
+            "aggregate_ms": r["aggregate_ms"], "aggregate_ms_last_rank": r["aggregate_ms_last_rank"],
+            "images_per_s": r["images_per_s"],
             "busy_max_over_mean": max(busy) / (sum(busy) / len(busy)),
             "round_ms_over_balanced_ideal": r["round_ms"] / (sum(loads) / world / rate * 1e3),
             "mean_client_loss": r["mean_client_loss"],
