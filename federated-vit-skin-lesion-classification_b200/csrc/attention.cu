@@ -535,8 +535,12 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
   FV_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "fv_attention_fwd: pointers must be 16-byte aligned");
   if (use_tc_attention(tokens)) {
-    const char* e = getenv("FEDVIT_ATTN_FWD");  // v1 = one thread per query row (first generation); read per call
-    const bool v1 = e != nullptr && e[0] == 'v' && e[1] == '1';
+    // FEDVIT_ATTN_FWD=v2: two threads per query row (attention_fwd2.cu) — bit-for-bit the same softmax
+    // arithmetic, parity-green, and as measured no faster (105.5 vs 103.4 us at 256 x 197 x 12: eight instead
+    // of four softmax warps per CTA do not raise any pipe's utilisation, profiles/r2_attn_variants.txt), so
+    // the first-generation kernel stays the default; read per call so one process can A/B them
+    const char* e = getenv("FEDVIT_ATTN_FWD");
+    const bool v1 = !(e != nullptr && e[0] == 'v' && e[1] == '2');
     return v1 ? attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream))
               : attention_tc_fwd2(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
   }
