@@ -525,3 +525,42 @@ def test_fedavg_round_with_metadata_branch_averages_running_stats_vs_oracle(gold
         if v.is_floating_point():
             err = float((v.detach().double().cpu() - want[k].double()).norm())
             assert err < 1e-2 * max(float(want[k].double().norm()), upd), k
+
+
+# ------------------------------------------------------------------------------------------------
+# second-generation attention kernels (opt-in: FEDVIT_ATTN_FWD=v2 / FEDVIT_ATTN_BWD=v2)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (3, 64, 1), (2, 65, 2), (1, 1, 1), (2, 256, 2), (4, 129, 2),
+                                   (1, 16, 1), (3, 200, 1), (40, 197, 12)])
+def test_second_generation_attention_kernels_vs_fp64(B, N, H, monkeypatch):
+    """attn_tc_fwd2_kernel (two threads per query row) and attn_tc_bwd2_kernel (keys on lanes: P^T as the
+    TMEM A operand of dV, dS^T through shared memory once) against an fp64 reference over ragged shapes, and
+    against the first-generation kernels they can replace (same outputs up to bf16 rounding)."""
+    import math
+
+    g = torch.Generator(device="cuda").manual_seed(N)
+    qkv = torch.randn(B * N, 3 * H * 64, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B * N, H * 64, device=DEV, generator=g).bfloat16()
+    scale = 1.0 / math.sqrt(64)
+    q, k, v = (qkv.double().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)[i].clone().requires_grad_(True) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * scale
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, H * 64)
+    o.backward(dout.double())
+    ref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B * N, 3, H * 64)
+    monkeypatch.setenv("FEDVIT_ATTN_FWD", "v1")
+    out1, lse1 = ops.attention_fwd(qkv, B, N, H, scale)
+    monkeypatch.setenv("FEDVIT_ATTN_FWD", "v2")
+    out2, lse2 = ops.attention_fwd(qkv, B, N, H, scale)
+    assert rel_err(out2, o.detach()) < 5e-3 and rel_err(lse2, torch.logsumexp(s.detach(), -1)) < 1e-5
+    assert rel_err(out2, out1) < 1e-2 and torch.equal(ops.attention_fwd(qkv, B, N, H, scale)[0], out2)
+    monkeypatch.setenv("FEDVIT_ATTN_BWD", "v2")
+    d2 = ops.attention_bwd(qkv, out2, dout, lse2, B, N, H, scale).float().view(B * N, 3, H * 64)
+    scale_ref = float(ref.norm()) + 1e-6 * float(dout.double().norm())  # N == 1: dq, dk are exactly 0
+    for i, name in enumerate("qkv"):
+        err = float((d2[:, i].double().cpu() - ref[:, i].cpu()).norm())
+        assert err < 1e-2 * max(float(ref[:, i].norm()), 1e-3 * scale_ref), name
+    again = ops.attention_bwd(qkv, out2, dout, lse2, B, N, H, scale).float().view(B * N, 3, H * 64)
+    assert torch.equal(again, d2)  # no atomics anywhere on the path
+    monkeypatch.setenv("FEDVIT_ATTN_BWD", "v1")
+    d1 = ops.attention_bwd(qkv, out2, dout, lse2, B, N, H, scale).float().view(B * N, 3, H * 64)
+    assert float((d2 - d1).norm()) < 1e-2 * max(float(d1.norm()), 1e-3 * scale_ref)
