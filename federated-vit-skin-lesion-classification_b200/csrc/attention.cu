@@ -490,6 +490,11 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
 int attention_tc_fwd2(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
                       float scale, cudaStream_t stream);
 
+// third-generation forward (attention_fwd3.cu): next tile's score MMA behind this tile's PV MMA, pipelined
+// tensor-memory loads, early PV start, rotated ragged tile; N <= 208
+int attention_tc_fwd3(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
+                      float scale, cudaStream_t stream);
+
 // second-generation backward, keys on lanes (attention_bwd2.cu); FEDVIT_ATTN_BWD=v1 keeps the first kernel
 int attention_tc_bwd2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                       int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
@@ -541,6 +546,8 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
     // the first-generation kernel stays the default; read per call so one process can A/B them
     const char* e = getenv("FEDVIT_ATTN_FWD");
     const bool v1 = !(e != nullptr && e[0] == 'v' && e[1] == '2');
+    if (e != nullptr && e[0] == 'v' && e[1] == '3' && tokens <= 208)
+      return attention_tc_fwd3(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
     return v1 ? attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream))
               : attention_tc_fwd2(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
   }

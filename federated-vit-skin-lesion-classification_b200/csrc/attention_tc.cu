@@ -35,6 +35,29 @@ struct AttnTcParams {
   float* lse;
 };
 
+#ifdef ATC_TRACE
+// measurement build (tools/build_variants.py ... trace:-DATC_TRACE): SM-clock timestamps of the first tiles of
+// four CTAs — [cta 0..3][tile 0..31][event 0..7]; events 0-4 softmax warp 0 (S ready, pass 1 done, P written,
+// O ready, row stored), 5-6 MMA warp (S issued, PV issued), 7 = smid. Read back with fv_debug_read_trace.
+__device__ long long g_atc_trace[4][32][8];
+__device__ __forceinline__ void atc_stamp(int gt, int ev) {
+  const int c = blockIdx.x == 0 ? 0 : blockIdx.x == 1 ? 1 : blockIdx.x == 148 ? 2 : blockIdx.x == 149 ? 3 : -1;
+  if (c >= 0 && gt < 32) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    g_atc_trace[c][gt][ev] = t;
+    if (ev == 0) {
+      uint32_t sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      g_atc_trace[c][gt][7] = sm;
+    }
+  }
+}
+#define ATC_STAMP(gt, ev) do { if (lane == 0) atc_stamp(gt, ev); } while (0)
+#else
+#define ATC_STAMP(gt, ev) do { } while (0)
+#endif
+
 __device__ __forceinline__ float atc_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -125,6 +148,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_fence_after();
         // S = Q K^T : both operands K-major (head dim contiguous), 4 steps of K = 16
         const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + t * ATC_Q * 128), 16, 1024);
+        ATC_STAMP(gt, 5);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
@@ -135,6 +159,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(bar_p, gt & 1);
         if (t == 0) mbar_wait(bar_v, n & 1);
         tc_fence_after();
+        ATC_STAMP(gt, 6);
         // O = P V : A = P from TMEM (16 keys = 8 packed columns per step), B = V MN-major
         if (elect_one()) {
           for (int k = 0; k < ksteps; ++k)
@@ -160,6 +185,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         float mx = -INFINITY, sum = 0.f;
         mbar_wait(bar_s, ph);
         tc_fence_after();
+        if (warp == 0) ATC_STAMP(gt, 0);
         if (warp_live) {
           for (int c = 0; c < nchunks; ++c) {
             uint32_t r[32];
@@ -175,6 +201,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
           }
           const float mxs = mx * sl2;
+          if (warp == 0) ATC_STAMP(gt, 1);
           for (int c = 0; c < nchunks; ++c) {
             uint32_t r[32], pk[16];
             tmem_ld_32x32(taddr + c * 32, r);
@@ -202,9 +229,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         tc_fence_before();
         mbar_arrive(bar_p);
+        if (warp == 0) ATC_STAMP(gt, 2);
 
         mbar_wait(bar_o, ph);
         tc_fence_after();
+        if (warp == 0) ATC_STAMP(gt, 3);
         uint32_t o0[32], o1[32];
         if (warp_live) {
           tmem_ld_32x32(taddr + 128, o0);
@@ -227,6 +256,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           for (int j = 0; j < 4; ++j) st_v8(dst + j * 16, w + j * 8);
           p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = mx * p.scale + logf(sum);
         }
+        if (warp == 0) ATC_STAMP(gt, 4);
       }
     }
   }
@@ -1569,3 +1599,14 @@ int attention_tc_bwd_long(const void* qkv, const void* dout, const float* lse, c
 }
 
 }  // namespace fv
+
+#ifdef ATC_TRACE
+extern "C" int fv_debug_read_trace(long long* dst, int64_t n) {
+  cudaDeviceSynchronize();
+  const size_t bytes = static_cast<size_t>(n) * sizeof(long long);
+  return cudaMemcpyFromSymbol(dst, fv::g_atc_trace, bytes < sizeof(fv::g_atc_trace) ? bytes : sizeof(fv::g_atc_trace)) ==
+                 cudaSuccess
+             ? 0
+             : -2;
+}
+#endif

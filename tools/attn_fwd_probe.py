@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Forward attention kernels (FEDVIT_ATTN_FWD = v1 | v2 | v3) on a B200: parity against an fp64 reference over
+ragged shapes and CUDA-event timings with L2 flushed between iterations.
+
+    python tools/attn_fwd_probe.py [--iters 20] [--versions v1,v3]
+"""
+import argparse
+import math
+import os
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import fedvit_b200  # noqa: F401,E402
+from fedvit_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def check(B, N, H, versions, spread=1.0):
+    g = torch.Generator(device=DEV).manual_seed(N)
+    qkv = (torch.randn(B * N, 3 * H * 64, device=DEV, generator=g) * spread).bfloat16()
+    scale = 1.0 / math.sqrt(64)
+    q, k, v = (qkv.double().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)[i] for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * scale
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, H * 64)
+    lse_ref = torch.logsumexp(s, -1)
+    ok = True
+    msg = []
+    for ver in versions:
+        os.environ["FEDVIT_ATTN_FWD"] = ver
+        out, lse = ops.attention_fwd(qkv, B, N, H, scale)
+        again, _ = ops.attention_fwd(qkv, B, N, H, scale)
+        torch.cuda.synchronize()
+        e, le, rep = rel(out, o), rel(lse, lse_ref), bool(torch.equal(out, again))
+        good = e < 5e-3 and le < 1e-5 and rep
+        ok &= good
+        msg.append(f"{ver}: out {e:.2e} lse {le:.2e} repro {rep}" + ("" if good else "  <-- BAD"))
+    print(f"B={B} N={N} H={H} spread={spread}: " + " | ".join(msg), flush=True)
+    return ok
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()  # 256 MB > L2: cold operands every iteration
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--versions", default="v1,v3")
+    ap.add_argument("--no-check", action="store_true")
+    a = ap.parse_args()
+    versions = a.versions.split(",")
+    ok = True
+    if not a.no_check:
+        for shape in [(2, 197, 3), (3, 64, 1), (2, 65, 2), (1, 1, 1), (1, 16, 1), (2, 17, 2), (4, 129, 2), (3, 200, 1),
+                      (2, 208, 2), (2, 180, 1), (5, 150, 3), (2, 33, 1), (40, 197, 12), (300, 197, 12)]:
+            ok &= check(*shape, versions)
+        ok &= check(8, 197, 12, versions, spread=4.0)
+    for B, N, H in [(256, 197, 12), (64, 197, 12), (1024, 197, 3)]:
+        qkv = torch.randn(B * N, 3 * H * 64, device=DEV).bfloat16()
+        row = []
+        for ver in versions:
+            os.environ["FEDVIT_ATTN_FWD"] = ver
+            row.append(f"{ver} {timeit(lambda: ops.attention_fwd(qkv, B, N, H, 0.125), a.iters):7.1f} us")
+        print(f"forward ({B}, {N}, {H}): " + "   ".join(row), flush=True)
+    print("PARITY", "OK" if ok else "FAILED")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
