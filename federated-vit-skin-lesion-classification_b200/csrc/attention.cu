@@ -495,6 +495,11 @@ int attention_tc_fwd2(const void* qkv, void* out, float* lse, int64_t batch, int
 int attention_tc_fwd3(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
                       float scale, cudaStream_t stream);
 
+// fourth-generation forward (attention_fwd4.cu): one pass over the scores (no row-maximum pass), softmax and
+// read-out on different warps, two score accumulators, two shared-memory stages; N <= 208
+int attention_tc_fwd4(const void* qkv, void* out, float* lse, int64_t batch, int64_t tokens, int64_t heads,
+                      float scale, cudaStream_t stream);
+
 // second-generation backward, keys on lanes (attention_bwd2.cu); FEDVIT_ATTN_BWD=v1 keeps the first kernel
 int attention_tc_bwd2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                       int64_t batch, int64_t tokens, int64_t heads, float scale, cudaStream_t stream);
@@ -546,6 +551,8 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
     // the first-generation kernel stays the default; read per call so one process can A/B them
     const char* e = getenv("FEDVIT_ATTN_FWD");
     const bool v1 = !(e != nullptr && e[0] == 'v' && e[1] == '2');
+    if (e != nullptr && e[0] == 'v' && e[1] == '4' && tokens <= 208 && scale > 0.f)
+      return attention_tc_fwd4(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
     if (e != nullptr && e[0] == 'v' && e[1] == '3' && tokens <= 208)
       return attention_tc_fwd3(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
     return v1 ? attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream))

@@ -214,9 +214,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on the barrier; a stall longer than ~2 s of SM clocks is a protocol bug, so trap (the
-// launch then fails with an error instead of hanging the GPU).
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or ~10 ms pass,
+// instead of returning after the short default limit. A loop over the plain form re-issues the test (plus the
+// loop's own bookkeeping) thousands of times per wait and takes issue slots from the warps that share the
+// scheduler — the softmax warps of the attention kernels ran at half speed next to three spinning warps
+// (profiles/r2_attn_trace.txt).
+__device__ __forceinline__ bool mbar_try_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+// Wait on the barrier; a stall longer than ~2 s of SM clocks is a protocol bug, so trap (the launch then fails
+// with an error instead of hanging the GPU).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef FV_MBAR_SPIN
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
@@ -226,6 +243,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+#else
+  if (mbar_try_wait_parked(bar, parity)) return;
+  long long t0, t1;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
+  while (!mbar_try_wait_parked(bar, parity)) {
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1));
+    if (t1 - t0 > 4000000000LL) {
+      printf("fedvit: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+#endif
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

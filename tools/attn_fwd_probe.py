@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Forward attention kernels (FEDVIT_ATTN_FWD = v1 | v2 | v3) on a B200: parity against an fp64 reference over
+"""Forward attention kernels (FEDVIT_ATTN_FWD = v1 | v2 | v3 | v4) on a B200: parity against an fp64 reference over
 ragged shapes and CUDA-event timings with L2 flushed between iterations.
 
     python tools/attn_fwd_probe.py [--iters 20] [--versions v1,v3]
@@ -24,9 +24,12 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def check(B, N, H, versions, spread=1.0):
+def check(B, N, H, versions, spread=1.0, late_keys=1.0):
     g = torch.Generator(device=DEV).manual_seed(N)
-    qkv = (torch.randn(B * N, 3 * H * 64, device=DEV, generator=g) * spread).bfloat16()
+    qkv = (torch.randn(B * N, 3 * H * 64, device=DEV, generator=g) * spread)
+    if late_keys != 1.0:  # keys from token 40 on much larger than the first 32: v4's shift has to be raised
+        qkv.view(B, N, 3, H * 64)[:, 40:, 1] *= late_keys
+    qkv = qkv.bfloat16()
     scale = 1.0 / math.sqrt(64)
     q, k, v = (qkv.double().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)[i] for i in range(3))
     s = (q @ k.transpose(-1, -2)) * scale
@@ -43,7 +46,7 @@ def check(B, N, H, versions, spread=1.0):
         good = e < 5e-3 and le < 1e-5 and rep
         ok &= good
         msg.append(f"{ver}: out {e:.2e} lse {le:.2e} repro {rep}" + ("" if good else "  <-- BAD"))
-    print(f"B={B} N={N} H={H} spread={spread}: " + " | ".join(msg), flush=True)
+    print(f"B={B} N={N} H={H} spread={spread} late_keys={late_keys}: " + " | ".join(msg), flush=True)
     return ok
 
 
@@ -67,7 +70,7 @@ def timeit(fn, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--versions", default="v1,v3")
+    ap.add_argument("--versions", default="v1,v4")
     ap.add_argument("--no-check", action="store_true")
     a = ap.parse_args()
     versions = a.versions.split(",")
@@ -77,6 +80,9 @@ def main():
                       (2, 208, 2), (2, 180, 1), (5, 150, 3), (2, 33, 1), (40, 197, 12), (300, 197, 12)]:
             ok &= check(*shape, versions)
         ok &= check(8, 197, 12, versions, spread=4.0)
+        ok &= check(4, 197, 3, versions, spread=2.0, late_keys=40.0)
+        ok &= check(3, 150, 2, versions, spread=3.0, late_keys=25.0)
+        ok &= check(2, 100, 2, versions, spread=6.0, late_keys=8.0)
     for B, N, H in [(256, 197, 12), (64, 197, 12), (1024, 197, 3)]:
         qkv = torch.randn(B * N, 3 * H * 64, device=DEV).bfloat16()
         row = []
