@@ -545,18 +545,17 @@ extern "C" int fv_attention_fwd(const void* qkv, void* out, float* lse, int dtyp
   FV_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "fv_attention_fwd: pointers must be 16-byte aligned");
   if (use_tc_attention(tokens)) {
-    // FEDVIT_ATTN_FWD=v2: two threads per query row (attention_fwd2.cu) — bit-for-bit the same softmax
-    // arithmetic, parity-green, and as measured no faster (105.5 vs 103.4 us at 256 x 197 x 12: eight instead
-    // of four softmax warps per CTA do not raise any pipe's utilisation, profiles/r2_attn_variants.txt), so
-    // the first-generation kernel stays the default; read per call so one process can A/B them
+    // N <= 208 (ViT @ 224: 197): the fourth-generation kernel (attention_fwd4.cu: one pass over the scores, eight
+    // softmax warps on 16-lane fragments, read-out on its own warps) — 85 vs 99 us at 256 x 197 x 12 alone,
+    // 105 vs 113 us inside a step. FEDVIT_ATTN_FWD = v1 | v2 | v3 selects the earlier generations (v1 also
+    // serves 208 < N <= 256); read per call so one process can A/B them
     const char* e = getenv("FEDVIT_ATTN_FWD");
-    const bool v1 = !(e != nullptr && e[0] == 'v' && e[1] == '2');
-    if (e != nullptr && e[0] == 'v' && e[1] == '4' && tokens <= 208 && scale > 0.f)
-      return attention_tc_fwd4(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
-    if (e != nullptr && e[0] == 'v' && e[1] == '3' && tokens <= 208)
-      return attention_tc_fwd3(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
-    return v1 ? attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream))
-              : attention_tc_fwd2(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));
+    const char ver = (e != nullptr && e[0] == 'v') ? e[1] : '4';
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ver == '4' && tokens <= 208 && scale > 0.f) return attention_tc_fwd4(qkv, out, lse, batch, tokens, heads, scale, st);
+    if (ver == '3' && tokens <= 208) return attention_tc_fwd3(qkv, out, lse, batch, tokens, heads, scale, st);
+    if (ver == '2') return attention_tc_fwd2(qkv, out, lse, batch, tokens, heads, scale, st);
+    return attention_tc_fwd(qkv, out, lse, batch, tokens, heads, scale, st);
   }
   if (use_tc_attention_long(tokens))
     return attention_tc_fwd_long(qkv, out, lse, batch, tokens, heads, scale, static_cast<cudaStream_t>(stream));

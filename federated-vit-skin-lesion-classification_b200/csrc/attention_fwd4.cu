@@ -9,36 +9,35 @@
 // CTA waits ~1000 cycles for the score MMA, reads the scores twice (row maximum 1350 cycles, exponentials 3400
 // with two CTAs sharing the pipe), waits 950 for the PV MMA and spends 900 on the read-out, and the two
 // co-resident CTAs fall into step instead of filling each other's gaps. Here, one CTA per SM:
-//   * eight softmax warps do nothing but the exponential pass, two per tensor-memory lane quarter: the pair shares
-//     the quarter's 32 rows and splits their keys (32-key chunks alternately), so each scheduler holds two
-//     softmax warps whose load latencies, shift checks and stores hide behind each other's exponentials
-//     (one warp per scheduler: 560 cycles per chunk where the MUFU pipe needs 256).
+//   * eight softmax warps do nothing but the exponential pass, two per tensor-memory lane quarter. Each owns 16
+//     whole rows of the tile (tcgen05.ld / st in the 16-lane shapes: a row is spread over four threads as in an
+//     MMA accumulator fragment, a thread holds two rows x 16 of every 64 keys), so each scheduler holds two
+//     softmax warps whose load latencies, shift checks and stores hide behind each other's exponentials (one
+//     warp per scheduler: 560 cycles per 32 exponentials where the MUFU pipe needs 256) and no two warps ever
+//     touch the same row: no barrier inside the pass, P goes over scores the warp itself has consumed.
 //   * the row maximum pass is gone: the shift of the softmax does not have to be the maximum, any m with
 //     max - m <= 64 keeps 2^(x - m) far from overflow and leaves the result unchanged (P is rounded to bf16 and
-//     accumulated in fp32: relative errors, no absolute ones). Both warps of a pair take m = the maximum of the
-//     row's first 32 keys, rounded up to an integer; a later chunk whose maximum (16 three-input max
-//     instructions in four chains, next to 32 exponentials) exceeds the warp's m by more than TAU = 64 — a 2^64
-//     ratio between keys, not seen outside adversarial inputs — takes a slow path that raises that warp's m and
-//     rescales its sum and the P it has written by the exact power of two. At the end of the tile the pair
-//     compares shifts through shared memory (one 64-thread named barrier) and the warp with the smaller one
-//     rescales once more, so the whole row ends on one m. The saved LSE is m ln2 + log(sum).
+//     accumulated in fp32: relative errors, no absolute ones). m = the maximum of the row's first 64 keys,
+//     rounded up to an integer; a later chunk whose maximum exceeds m by more than TAU = 64 — a 2^64 ratio
+//     between keys, not seen outside adversarial inputs — takes a slow path that raises m and rescales the sum
+//     and the P already written by the exact power of two. The saved LSE is m ln2 + log(sum).
 //   * two score accumulators in tensor memory: the MMA warp issues tile g + 2's QK^T right behind tile g's PV
 //     MMA, so the scores of the next tile are waiting when the softmax warps finish a tile.
 //   * four epilogue warps read O out of tensor memory, normalise and store it while the softmax warps are
 //     already in the next tile; the row statistics cross through shared memory.
 //   * Q, K, V of the next (batch, head) item land in a second shared-memory stage.
 //   * the ragged last query tile (69 of 128 rows at N = 197) is rotated over the four lane quarters per item as
-//     in the third-generation kernel, and the warps are decoupled (mbarriers only), so an idle pair moves on.
-//   * the pass is kept small (one unmasked 32-wide body per register buffer, one 16-wide ragged tail): with
-//     every chunk variant inlined at every call site it was 23 KB of straight-line code per loop iteration and
-//     ran at 3.5 cycles per instruction.
+//     in the third-generation kernel, and the warps are decoupled (mbarriers only), so an idle warp moves on.
+//   * the pass is kept small (one 64-key body per register buffer, one 16-key tail body): with every chunk
+//     variant inlined at every call site an earlier version was 23 KB of straight-line code per loop iteration
+//     and ran at 3.5 cycles per instruction.
 #include "common.cuh"
 
 namespace fv {
 
 namespace {
 
-constexpr int F4_SW = 8;                          // warps [0, 8) softmax (warp & 3 = lane quarter, warp >> 2 = key half),
+constexpr int F4_SW = 8;                          // warps [0, 8) softmax (warp & 3 = lane quarter, warp >> 2 = its 16-lane half),
                                                   // [F4_SW, F4_SW + 4) epilogue,
 constexpr int F4_W_MMA = F4_SW + 4;               // then MMA issue,
 constexpr int F4_W_TMA = F4_SW + 5;               // then TMEM alloc + TMA producer
@@ -46,13 +45,14 @@ constexpr int F4_THREADS = 32 * (F4_SW + 6);
 constexpr int F4_Q = 128;
 constexpr int F4_KV_MAX = 208;
 constexpr int F4_STAGE = 2 * F4_Q * 128 + 2 * F4_KV_MAX * 128;  // Q tiles, K, V of one item: 84 KiB
-constexpr int F4_SMEM = 2 * F4_STAGE + 4 * 256 * 8 + 2 * 512 * 4 + 256 + 1024;
+constexpr int F4_ONES = 16 * 128;  // one 16-key step of the "ones" column block appended to V (see the PV MMA)
+constexpr int F4_SMEM = 2 * F4_STAGE + F4_ONES + 4 * 128 * 8 + 256 + 1024;
 constexpr float F4_LOG2E = 1.4426950408889634f;
 constexpr float F4_LN2 = 0.6931471805599453f;
 constexpr float F4_TAU = 64.f;  // a chunk maximum more than 2^TAU above the row's shift raises the shift
 constexpr uint32_t F4_T_S0 = 0;    // score / P buffer of even tiles: columns [0, 208)
 constexpr uint32_t F4_T_S1 = 224;  // odd tiles: [224, 432)
-constexpr uint32_t F4_T_O = 448;   // O accumulator: [448, 512)
+constexpr uint32_t F4_T_O = 432;   // O accumulator: [432, 496) + the row sums of the rounded P in column 496
 
 struct Fwd4Params {
   int N, H, kw;  // tokens, heads, keys rounded up to 16 (<= 208)
@@ -122,17 +122,45 @@ __device__ __forceinline__ float f4_max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-__device__ __forceinline__ void f4_ld16(uint32_t taddr, uint32_t* r) {
+// ---- 16-lane tensor-memory shapes: the warp reads / writes lanes [l0, l0 + 16) (l0 = the lane field of the
+// address); thread t holds row t / 4 and row t / 4 + 8 of them.
+// 16x256b.xN: N x 8 fp32 columns; registers 4 i .. 4 i + 3 = (row A, columns 8 i + 2 (t % 4) + {0, 1}), (row B, same)
+__device__ __forceinline__ void f4_ld64(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void f4_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+__device__ __forceinline__ void f4_ld16(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// 16x128b.xN: N x 4 packed-bf16 columns; registers 2 i, 2 i + 1 = (row A, column 4 i + t % 4), (row B, same) — the
+// packed pair of a 16x256b repetition lands exactly there
+__device__ __forceinline__ void f4_st64(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void f4_st16(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void f4_ldp16(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x2.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
                : "memory");
 }
 // wait for the outstanding tensor-memory loads; the buffer is an in/out operand so that no use of it can be
@@ -147,104 +175,94 @@ __device__ __forceinline__ void f4_ld_wait(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void f4_ld_wait8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float f4_quad_max(float v) {  // over the four threads that share a row
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
 
-// the softmax state of one row (one thread)
-struct F4Row {
-  float m;    // the shift, an integer in the log2 domain (x = score * scale * log2e)
-  float sum;  // sum of 2^(x - m)
+// the softmax state of a thread's two rows (the four threads of a row carry the same shift and partial sums)
+struct F4Rows {
+  float mA, mB;  // the shifts, integers in the log2 domain (x = score * scale * log2e)
+  float sA, sB;  // this thread's share of the sums of 2^(x - m)
 };
 
-// Slow path: scale what a warp has produced for its rows so far — the sum and the packed P of its first `own8`
-// groups of 16 keys, which sit at tp + 8 j — by the exact 2^(m - m_new) for the lanes with `raise` set.
-// Returns (m', scaled sum).
-__device__ __noinline__ float2 f4_rescale(uint32_t tp, int own8, bool raise, float m_new, float m, float sum) {
-  m_new = raise ? m_new : m;
-  const float r = f4_ex2(m - m_new);  // 1 for the lanes that keep their shift
-  tmem_st_wait();                     // the P stores issued so far have to land before they are read back
-  for (int j = 0; j < own8; ++j) {
-    uint32_t pk[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(pk[0]), "=r"(pk[1]), "=r"(pk[2]), "=r"(pk[3]), "=r"(pk[4]), "=r"(pk[5]), "=r"(pk[6]), "=r"(pk[7])
-                 : "r"(tp + j * 8)
-                 : "memory");
+// Slow path: raise the shifts of the rows whose chunk maximum (cA, cB: this thread's share, log2 domain) is more
+// than TAU above them, and scale what the warp has produced for those rows so far — the partial sums and the
+// packed P of its first `done16` groups of 16 keys at tp — by the exact 2^(m - m').
+__device__ __noinline__ float4 f4_raise(uint32_t tp, int done16, float cA, float cB, float4 st) {  // st = (mA, mB, sA, sB)
+  cA = f4_quad_max(cA);
+  cB = f4_quad_max(cB);
+  const float mA = cA > st.x + F4_TAU ? ceilf(cA) : st.x;
+  const float mB = cB > st.y + F4_TAU ? ceilf(cB) : st.y;
+  const float rA = f4_ex2(st.x - mA), rB = f4_ex2(st.y - mB);  // 1 for the rows that keep their shift
+  tmem_st_wait();  // the P stores issued so far have to land before they are read back
+  for (int j = 0; j < done16; ++j) {
+    uint32_t pk[4];
+    f4_ldp16(tp + j * 8, pk);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const float2 v = unpack_bf16(pk[i]);
+      const float r = (i & 1) ? rB : rA;
       pk[i] = pack_bf16(v.x * r, v.y * r);
     }
-    f4_st8(tp + j * 8, pk);
+    f4_st16(tp + j * 8, pk);
   }
   tmem_st_wait();
-  return make_float2(m_new, sum * r);
+  return make_float4(mA, mB, st.z * rA, st.w * rB);
 }
 
-// maximum of W (16 or 32) scores, four independent FMNMX3 chains
+// this thread's share of the maxima of its two rows over W (64 or 16) keys: registers 4 i + {0, 1} row A, {2, 3} row B
 template <int W>
-__device__ __forceinline__ float f4_max(const uint32_t* r) {
-  float c0 = f4_max3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
-  float c1 = f4_max3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
-  float c2 = f4_max3(__uint_as_float(r[6]), __uint_as_float(r[7]), __uint_as_float(r[8]));
-  float c3 = f4_max3(__uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
+__device__ __forceinline__ void f4_max(const uint32_t* r, float& cA, float& cB) {
+  cA = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
+  cB = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
 #pragma unroll
-  for (int i = 12; i + 7 < W; i += 8) {
-    c0 = f4_max3(c0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-    c1 = f4_max3(c1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-    c2 = f4_max3(c2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-    c3 = f4_max3(c3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
-  }
-  c0 = f4_max3(c0, __uint_as_float(r[W - 4]), __uint_as_float(r[W - 3]));
-  c1 = f4_max3(c1, __uint_as_float(r[W - 2]), __uint_as_float(r[W - 1]));
-  return fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
-}
-// shift check before a piece's exponentials (cmx = its maximum in the log2 domain; own8 = 16-key groups this warp
-// has already written at tp); called with no tensor-memory load in flight — the slow path is a function call, and
-// registers an asynchronous load still targets must not be live (or reused) across it
-__device__ __forceinline__ void f4_check(float cmx, int own8, uint32_t tp, F4Row& row) {
-  if (__any_sync(0xffffffffu, cmx > row.m + F4_TAU)) {
-    const float2 ms = f4_rescale(tp, own8, cmx > row.m + F4_TAU, ceilf(cmx), row.m, row.sum);
-    row.m = ms.x;
-    row.sum = ms.y;
+  for (int i = 1; i < W / 8; ++i) {
+    cA = f4_max3(cA, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]));
+    cB = f4_max3(cB, __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
   }
 }
-// exponentials of W scores with the row's shift: packed bf16 P into pk[0 .. W/2), row sum
+// shift check before a chunk's exponentials (done16 = 16-key groups whose P this warp has already written);
+// called with no tensor-memory load in flight — the slow path is a function call, and registers an asynchronous
+// load still targets must not be live (or reused) across it
+__device__ __forceinline__ void f4_check(float cA, float cB, float sl2, int done16, uint32_t tp, F4Rows& rows) {
+  cA *= sl2;
+  cB *= sl2;
+  if (__any_sync(0xffffffffu, cA > rows.mA + F4_TAU || cB > rows.mB + F4_TAU)) {
+    const float4 st = f4_raise(tp, done16, cA, cB, make_float4(rows.mA, rows.mB, rows.sA, rows.sB));
+    rows.mA = st.x;
+    rows.mB = st.y;
+    rows.sA = st.z;
+    rows.sB = st.w;
+  }
+}
+// exponentials of W keys of the two rows: packed bf16 P into pk[0 .. W/4) in the 16x128b register order, sums
 template <int W>
-__device__ __forceinline__ void f4_exp(const uint32_t* r, float sl2, F4Row& row, uint32_t* pk) {
-  const float ms = row.m;
-  float s0 = 0.f, s1 = 0.f;
+__device__ __forceinline__ void f4_exp(const uint32_t* r, float sl2, F4Rows& rows, uint32_t* pk) {
+  const float mA = rows.mA, mB = rows.mB;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < W; i += 2) {
-    const float p0 = f4_ex2(fmaf(__uint_as_float(r[i]), sl2, -ms));
-    const float p1 = f4_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -ms));
-    s0 += p0;
-    s1 += p1;
-    pk[i >> 1] = pack_bf16(p0, p1);
+  for (int i = 0; i < W / 8; ++i) {
+    const float p0 = f4_ex2(fmaf(__uint_as_float(r[4 * i]), sl2, -mA));
+    const float p1 = f4_ex2(fmaf(__uint_as_float(r[4 * i + 1]), sl2, -mA));
+    const float p2 = f4_ex2(fmaf(__uint_as_float(r[4 * i + 2]), sl2, -mB));
+    const float p3 = f4_ex2(fmaf(__uint_as_float(r[4 * i + 3]), sl2, -mB));
+    a0 += p0;
+    a1 += p1;
+    b0 += p2;
+    b1 += p3;
+    pk[2 * i] = pack_bf16(p0, p1);
+    pk[2 * i + 1] = pack_bf16(p2, p3);
   }
-  row.sum += s0 + s1;
-}
-// maximum of the first nv (1 .. 16) of 16 scores: the last 16 columns of the key range hold the ragged end
-__device__ __forceinline__ float f4_max_masked(const uint32_t* r, int nv) {
-  float cm = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (i < nv) cm = fmaxf(cm, __uint_as_float(r[i]));
-  return cm;
-}
-// ... and their exponentials: keys outside the sequence get P = 0
-__device__ __forceinline__ void f4_exp_masked(const uint32_t* r, int nv, float sl2, F4Row& row, uint32_t* pk) {
-  const float ms = row.m;
-  float s0 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; i += 2) {
-    const float p0 = i < nv ? f4_ex2(fmaf(__uint_as_float(r[i]), sl2, -ms)) : 0.f;
-    const float p1 = i + 1 < nv ? f4_ex2(fmaf(__uint_as_float(r[i + 1]), sl2, -ms)) : 0.f;
-    s0 += p0 + p1;
-    pk[i >> 1] = pack_bf16(p0, p1);
-  }
-  row.sum += s0;
-}
-__device__ __forceinline__ void f4_pair_sync(int quarter) {  // the two softmax warps of a lane quarter
-  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+  rows.sA += a0 + a1;
+  rows.sB += b0 + b1;
 }
 
 __global__ void __launch_bounds__(F4_THREADS, 1)
@@ -253,9 +271,9 @@ attn_tc_fwd4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // stage s: Q tiles (2 x 16 KiB) | K (26 KiB) | V (26 KiB)
-  float2* stats = reinterpret_cast<float2*>(smem + 2 * F4_STAGE);  // [4][2][128] (m, sum of the key half), tile g & 3
-  float* xm = reinterpret_cast<float*>(smem + 2 * F4_STAGE + 4 * 256 * 8);  // [2][2][2][128] what the pair exchanges, tile g & 1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * F4_STAGE + 4 * 256 * 8 + 2 * 512 * 4);
+  uint8_t* ones = smem + 2 * F4_STAGE;  // 16 keys x 64 columns (MN-major, 128B swizzle): column 0 = 1, the rest 0
+  float2* stats = reinterpret_cast<float2*>(ones + F4_ONES);  // [4][128] (m, sum) of the rows of tile g & 3
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + F4_ONES + 4 * 128 * 8);
   uint64_t* bar_qk = bars + 0;      // [2] Q tiles + K of the stage landed
   uint64_t* bar_v = bars + 2;       // [2] V landed
   uint64_t* bar_qkfree = bars + 4;  // [2] the item's last score MMA has retired
@@ -287,6 +305,14 @@ attn_tc_fwd4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     mbar_init(bar_o, 1);
     mbar_init(bar_ofree, 128);
     fence_mbar_init();
+  }
+  if (threadIdx.x < 128) {
+    // row r of the block is 128 bytes; the swizzle puts its first 16-byte chunk (columns 0 .. 7) at chunk r % 8
+    uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
+    if (c == (r & 7)) z.x = 0x3f80u;  // bf16 1.0 in column 0
+    reinterpret_cast<uint4*>(ones)[threadIdx.x] = z;
+    fence_proxy_async_smem();  // written through the generic proxy, read by the tensor core
   }
   if (warp == F4_W_TMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -329,7 +355,11 @@ attn_tc_fwd4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   } else if (warp == F4_W_MMA) {
     // ------------------------------ MMA issue (whole warp, elected lane issues) -----------------
     const uint32_t idesc_s = make_idesc(kFmtBF16, 0, 0, F4_Q, p.kw);
-    const uint32_t idesc_o = make_idesc(kFmtBF16, 0, 1, F4_Q, 64);
+    // O = P [V | 1]: 16 columns more than the head, the first of them all ones — column 64 of the accumulator is
+    // the row sum of P exactly as the tensor core saw it (rounded to bf16), and O / that sum is a true convex
+    // combination of the value rows (normalising by the fp32 sum of the unrounded exponentials is off by the
+    // rounding of every P; with the row maximum no longer pinned to P = 1 a one-key row showed it: 0.4 %)
+    const uint32_t idesc_o = make_idesc(kFmtBF16, 0, 1, F4_Q, 80);
     auto issue_scores = [&](int g) {
       const int n = g / nqt, t = g % nqt, s = n & 1;
       if (t == 0) mbar_wait(bar_qk + s, (n >> 1) & 1);
@@ -356,14 +386,16 @@ attn_tc_fwd4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (t == 0) mbar_wait(bar_v + s, (n >> 1) & 1);
       if (g > 0) mbar_wait(bar_ofree, (g - 1) & 1);
       tc_fence_after();
-      const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + s * F4_STAGE) + (2 * F4_Q + F4_KV_MAX) * 128, 64 * 128, 1024);
+      const uint32_t sV = smem_u32(smem + s * F4_STAGE) + (2 * F4_Q + F4_KV_MAX) * 128;
+      const uint32_t s1 = smem_u32(ones);
       const uint32_t tp = tmem + ((g & 1) ? F4_T_S1 : F4_T_S0);
       F4_STAMP(g, 6);
       if (elect_one()) {
-        // P of key group k: the first warp of a pair packs its groups from column 0, the second from column 16 g0
-        const int g0 = p.kw >> 5;
+        // per 16-key step: V rows at sV + 2 KiB k; the second 64-column block of the operand ("leading" byte
+        // offset) always resolves to the one ones block
         for (int k = 0; k < (p.kw >> 4); ++k)
-          umma_bf16_ts(tmem + F4_T_O, tp + (k < g0 ? k * 8 : g0 * 16 + (k - g0) * 8), dv + 16 * k * 8, idesc_o, k > 0 ? 1u : 0u);
+          umma_bf16_ts(tmem + F4_T_O, tp + k * 8, make_smem_desc_sw128(sV + k * 2048, s1 - (sV + k * 2048), 1024), idesc_o,
+                       k > 0 ? 1u : 0u);
         umma_commit(bar_o);
         if (t == nqt - 1) umma_commit(bar_vfree + s);
       }
@@ -372,115 +404,98 @@ attn_tc_fwd4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
   } else if (warp < F4_SW) {
     // ------------------------------ softmax: one pass over the scores ---------------------------
-    // The pair of a lane quarter splits the keys in the middle (16-key groups [0, g0) and [g0, G)); each warp
-    // reads scores and writes P inside its own column range only — P of its group j over the first 8 columns of
-    // what it has already read — so no warp ever overwrites scores the other one still needs.
-    const int wq = warp & 3;     // TMEM lane quarter
-    const int half = warp >> 2;
+    const int wq = warp & 3;   // TMEM lane quarter
+    const int sub = warp >> 2; // its lanes [16 sub, 16 sub + 16)
+    const int qd = lane & 3;   // a row's four threads: thread qd holds columns 8 i + 2 qd + {0, 1}
     const float sl2 = p.scale * F4_LOG2E;
-    const int G = p.kw >> 4, g0 = G >> 1;
-    const int whole = half ? G - g0 - 1 : g0;  // this warp's 16-key groups that lie inside the sequence entirely;
-    const int nch = whole >> 1;                // as 32-wide chunks
-    const bool odd16 = (whole & 1) != 0;       // + one 16-wide piece; warp 1 then has the ragged last group
-    const int nv_last = p.N - (G - 1) * 16;    // keys of the sequence in it
+    const int n64 = (p.kw - 16) >> 6;          // 64-key chunks, none of them ragged
+    const int n16 = (p.kw - n64 * 64) >> 4;    // + 1 .. 4 groups of 16 keys, the last one holding the ragged end
+    const int nv_last = p.N - (p.kw - 16);     // keys of the sequence in it (1 .. 16)
     for (int g = 0; g < ntiles; ++g) {
       const int n = g / nqt, t = g % nqt;
       const int rot = (n + blockIdx.x) & 3;
-      const int rb = t == nqt - 1 ? (wq - rot) & 3 : wq;  // this pair's 32-row block of the tile
-      const bool warp_live = t * F4_Q + rb * 32 < p.N;     // warp-uniform, the same for both warps of the pair
-      const uint32_t tp = tmem + (static_cast<uint32_t>(wq * 32) << 16) + ((g & 1) ? F4_T_S1 : F4_T_S0) + half * g0 * 16;
+      const int rb = t == nqt - 1 ? (wq - rot) & 3 : wq;         // this quarter's 32-row block of the tile
+      const bool warp_live = t * F4_Q + rb * 32 + sub * 16 < p.N;  // warp-uniform
+      const uint32_t tp = tmem + (static_cast<uint32_t>(wq * 32 + sub * 16) << 16) + ((g & 1) ? F4_T_S1 : F4_T_S0);
       if (warp == 0) F4_STAMP(g, 0);
       mbar_wait(bar_s + (g & 1), (g >> 1) & 1);
       tc_fence_after();
       if (warp == 0) F4_STAMP(g, 1);
       if (warp_live) {
-        F4Row row;
-        row.sum = 0.f;
+        F4Rows rows;
+        rows.sA = rows.sB = 0.f;
         uint32_t a[32], bq[32];
-        float* xrow = xm + (g & 1) * 512 + wq * 32 + lane;  // [tile parity][start / end][half][128]
-        // ---- the pair's common shift: the maximum over both warps' first pieces, rounded up to an integer
-        float first = -INFINITY;
-        if (nch > 0) {
-          tmem_ld_32x32(tp, a);
+        // ---- 64-key chunks through two register buffers, the load of the next one in flight during the exponentials
+        if (n64 > 0) {
+          f4_ld64(tp, a);
           f4_ld_wait(a);
-          first = f4_max<32>(a);
-        } else if (odd16 || half == 1) {
-          f4_ld16(tp, a);
-          f4_ld_wait(a);
-          first = odd16 ? f4_max<16>(a) : f4_max_masked(a, nv_last);
         }
-        xrow[half * 128] = first;
-        f4_pair_sync(wq);
-        row.m = ceilf(fmaxf(first, xrow[(half ^ 1) * 128]) * sl2);
-        // ---- chunks through two register buffers, the load of the next one in flight during the exponentials
-        for (int k = 0; k < nch; k += 2) {
+        for (int k = 0; k < n64; k += 2) {
           uint32_t pk[16];
-          if (k > 0) {
-            f4_ld_wait(a);
-            F4_CSTAMP(k, 0);
-            f4_check(f4_max<32>(a) * sl2, 2 * k, tp, row);
+          float cA, cB;
+          if (k > 0) f4_ld_wait(a);
+          F4_CSTAMP(k, 0);
+          f4_max<64>(a, cA, cB);
+          if (k == 0) {  // the first 64 keys set the rows' shifts
+            rows.mA = ceilf(f4_quad_max(cA) * sl2);
+            rows.mB = ceilf(f4_quad_max(cB) * sl2);
+          } else {
+            f4_check(cA, cB, sl2, 4 * k, tp, rows);
           }
-          tmem_ld_32x32(tp + (k + 1) * 32, bq);  // unconditional (a branch here sinks the load below the exponentials)
+          f4_ld64(tp + (k + 1) * 64, bq);  // unconditional (a branch here sinks the load below the exponentials)
           F4_CSTAMP(k, 1);
-          f4_exp<32>(a, sl2, row, pk);
+          f4_exp<64>(a, sl2, rows, pk);
           F4_CSTAMP(k, 2);
-          tmem_st_32x16(tp + k * 16, pk);
+          f4_st64(tp + k * 32, pk);
           F4_CSTAMP(k, 3);
-          if (k + 1 < nch) {
+          if (k + 1 < n64) {
             f4_ld_wait(bq);
             F4_CSTAMP(k + 1, 0);
-            f4_check(f4_max<32>(bq) * sl2, 2 * k + 2, tp, row);
-            tmem_ld_32x32(tp + (k + 2) * 32, a);
+            f4_max<64>(bq, cA, cB);
+            f4_check(cA, cB, sl2, 4 * k + 4, tp, rows);
+            f4_ld64(tp + (k + 2) * 64, a);
             F4_CSTAMP(k + 1, 1);
-            f4_exp<32>(bq, sl2, row, pk);
+            f4_exp<64>(bq, sl2, rows, pk);
             F4_CSTAMP(k + 1, 2);
-            tmem_st_32x16(tp + (k + 1) * 16, pk);
+            f4_st64(tp + (k + 1) * 32, pk);
             F4_CSTAMP(k + 1, 3);
           }
         }
-        if (nch > 0) {
-          // the look-ahead load of the loop's last iteration holds the columns after the chunks: the 16-wide
-          // pieces below (it may reach 16 columns past this warp's range — read, never used)
-          if (nch & 1) f4_ld_wait(bq);
-          else f4_ld_wait(a);
-        }
-        {
-          uint32_t pk[16];
-          uint32_t tl[32];  // static register names: a select per element instead of a run-time choice of array
-          const bool from_b = (nch & 1) != 0;
+        tmem_ld_wait();  // retires the loop's last (unused) look-ahead load before any call below
+        // ---- the remaining 16-key groups; in the last one the keys outside the sequence get P = 0
+        for (int j = 0; j < n16; ++j) {
+          uint32_t t8[8], pk[4];
+          const int done16 = n64 * 4 + j;
+          f4_ld16(tp + done16 * 16, t8);
+          f4_ld_wait8(t8);
+          if (j == n16 - 1) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tl[i] = from_b ? bq[i] : a[i];
-          int own8 = 2 * nch;
-          if (odd16) {
-            if (nch > 0) f4_check(f4_max<16>(tl) * sl2, own8, tp, row);
-            f4_exp<16>(tl, sl2, row, pk);
-            f4_st8(tp + own8 * 8, pk);
-            ++own8;
-          }
-          if (half == 1) {
-            if (nch == 0 && odd16) {  // the first load was 16 wide: fetch the ragged group
-              f4_ld16(tp + 16, tl + 16);
-              f4_ld_wait(tl);
+            for (int i = 0; i < 2; ++i) {
+              const int key = 8 * i + 2 * qd;
+              if (key >= nv_last) t8[4 * i] = t8[4 * i + 2] = 0xff800000u;  // -inf: exponential 0, no say in the maximum
+              if (key + 1 >= nv_last) t8[4 * i + 1] = t8[4 * i + 3] = 0xff800000u;
             }
-            uint32_t tr[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) tr[i] = odd16 ? tl[16 + i] : tl[i];
-            if (own8 > 0) f4_check(f4_max_masked(tr, nv_last) * sl2, own8, tp, row);
-            f4_exp_masked(tr, nv_last, sl2, row, pk);
-            f4_st8(tp + own8 * 8, pk);
-            ++own8;
           }
-          // ---- the pair settles on one shift per row (they differ only if one of the two raised its own)
-          xrow[256 + half * 128] = row.m;
-          f4_pair_sync(wq);
-          const float m_star = fmaxf(row.m, xrow[256 + (half ^ 1) * 128]);
-          if (__any_sync(0xffffffffu, m_star != row.m)) {
-            const float2 ms = f4_rescale(tp, own8, m_star != row.m, m_star, row.m, row.sum);
-            row.m = ms.x;
-            row.sum = ms.y;
+          float cA, cB;
+          f4_max<16>(t8, cA, cB);
+          if (done16 == 0) {
+            rows.mA = ceilf(f4_quad_max(cA) * sl2);
+            rows.mB = ceilf(f4_quad_max(cB) * sl2);
+          } else {
+            f4_check(cA, cB, sl2, done16, tp, rows);
           }
+          f4_exp<16>(t8, sl2, rows, pk);
+          f4_st16(tp + done16 * 8, pk);
         }
-        stats[((g & 3) * 2 + half) * 128 + wq * 32 + lane] = make_float2(row.m, row.sum);
+        // ---- row sums over the four threads of a row
+        rows.sA += __shfl_xor_sync(0xffffffffu, rows.sA, 1);
+        rows.sB += __shfl_xor_sync(0xffffffffu, rows.sB, 1);
+        rows.sA += __shfl_xor_sync(0xffffffffu, rows.sA, 2);
+        rows.sB += __shfl_xor_sync(0xffffffffu, rows.sB, 2);
+        if (qd == 0) {
+          stats[(g & 3) * 128 + wq * 32 + sub * 16 + (lane >> 2)] = make_float2(rows.mA, rows.sA);
+          stats[(g & 3) * 128 + wq * 32 + sub * 16 + (lane >> 2) + 8] = make_float2(rows.mB, rows.sB);
+        }
         tmem_st_wait();
       }
       tc_fence_before();
@@ -502,19 +517,19 @@ attn_tc_fwd4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(bar_o, g & 1);
       tc_fence_after();
       if (w4 == 0) F4_STAMP(g, 3);
-      uint32_t o0[32], o1[32];
+      uint32_t o0[32], o1[32], psum = 0;
       if (warp_live) {
         tmem_ld_32x32(to, o0);
         tmem_ld_32x32(to + 32, o1);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(psum) : "r"(to + 64) : "memory");
         tmem_ld_wait();
       }
       tc_fence_before();
       mbar_arrive(bar_ofree);
       if (warp_live && q < p.N) {
         // written before the row's arrival on bar_p, which the PV MMA behind bar_o waited for
-        const float2 st0 = stats[((g & 3) * 2 + 0) * 128 + w4 * 32 + lane];
-        const float2 st = make_float2(st0.x, st0.y + stats[((g & 3) * 2 + 1) * 128 + w4 * 32 + lane].y);
-        const float inv = 1.0f / st.y;
+        const float2 st = stats[(g & 3) * 128 + w4 * 32 + lane];
+        const float inv = 1.0f / __uint_as_float(psum);  // sum of the rounded P (st.y, the exact one, goes into the LSE)
         uint32_t w[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {

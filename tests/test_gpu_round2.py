@@ -564,3 +564,45 @@ def test_second_generation_attention_kernels_vs_fp64(B, N, H, monkeypatch):
     monkeypatch.setenv("FEDVIT_ATTN_BWD", "v1")
     d1 = ops.attention_bwd(qkv, out2, dout, lse2, B, N, H, scale).float().view(B * N, 3, H * 64)
     assert float((d2 - d1).norm()) < 1e-2 * max(float(d1.norm()), 1e-3 * scale_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# fourth-generation attention forward (default for N <= 208): one pass over the scores, shift from the first keys
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,H,spread,late", [(2, 197, 3, 1.0, 1.0), (3, 64, 1, 1.0, 1.0), (2, 65, 2, 1.0, 1.0),
+                                                (1, 1, 1, 1.0, 1.0), (1, 16, 1, 1.0, 1.0), (2, 17, 2, 1.0, 1.0),
+                                                (2, 33, 1, 1.0, 1.0), (4, 129, 2, 1.0, 1.0), (3, 200, 1, 1.0, 1.0),
+                                                (2, 208, 2, 1.0, 1.0), (5, 150, 3, 1.0, 1.0), (40, 197, 12, 1.0, 1.0),
+                                                (8, 197, 12, 4.0, 1.0), (4, 197, 3, 2.0, 40.0), (3, 150, 2, 3.0, 25.0),
+                                                (2, 100, 2, 6.0, 8.0)])
+def test_single_pass_attention_forward_vs_fp64(B, N, H, spread, late, monkeypatch):
+    """attn_tc_fwd4_kernel against an fp64 softmax(QK^T)V over ragged shapes — including inputs whose later keys
+    beat the first 64 by far more than 2^64 (``late``: keys from token 40 on scaled up), which send rows through
+    the shift-raising slow path — and against the first-generation two-pass kernel; the backward consumes its
+    LSE unchanged."""
+    import math
+
+    g = torch.Generator(device="cuda").manual_seed(1000 + N)
+    qkv = torch.randn(B * N, 3 * H * 64, device=DEV, generator=g) * spread
+    if late != 1.0:
+        qkv.view(B, N, 3, H * 64)[:, 40:, 1] *= late
+    qkv = qkv.bfloat16()
+    scale = 1.0 / math.sqrt(64)
+    q, k, v = (qkv.double().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)[i] for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * scale
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * N, H * 64)
+    monkeypatch.setenv("FEDVIT_ATTN_FWD", "v4")
+    n0 = _lib.kernel_launches(_lib.KERNEL_ATTN_FWD)
+    out4, lse4 = ops.attention_fwd(qkv, B, N, H, scale)
+    assert _lib.kernel_launches(_lib.KERNEL_ATTN_FWD) == n0 + 1
+    assert torch.isfinite(out4.float()).all() and torch.isfinite(lse4).all()
+    assert rel_err(out4, o) < 5e-3 and rel_err(lse4, torch.logsumexp(s, -1)) < 1e-5
+    assert torch.equal(ops.attention_fwd(qkv, B, N, H, scale)[0], out4)  # deterministic
+    monkeypatch.setenv("FEDVIT_ATTN_FWD", "v1")
+    out1, lse1 = ops.attention_fwd(qkv, B, N, H, scale)
+    assert rel_err(out4, out1) < 1e-2 and rel_err(lse4, lse1) < 1e-5
+    # the backward recomputes P from the saved LSE: same gradients from either forward
+    dout = torch.randn(B * N, H * 64, device=DEV, generator=g).bfloat16()
+    d4 = ops.attention_bwd(qkv, out4, dout, lse4, B, N, H, scale).float()
+    d1 = ops.attention_bwd(qkv, out1, dout, lse1, B, N, H, scale).float()
+    assert float((d4 - d1).norm()) <= 1e-2 * float(d1.norm()) + 1e-6
