@@ -352,6 +352,23 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv;
 };
 
+#ifdef ATC_TRACE
+// measurement build: SM-clock timestamps of math warp 0 of CTA 0 over its first 24 (key block, query tile) cells —
+// 0 arrives at the score wait, 1 scores there, 2 S / dP of both chunks read (bar_c), 3 math done, 4 previous MMA 2
+// retired (sP / sdS free), 5 P / dS stored (bar_p), 6 drains done
+__device__ long long g_atb_trace[24][8];
+#define ATB_STAMP(it, ev)                                              \
+  do {                                                                 \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (it) < 24) {            \
+      long long t_;                                                    \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_));               \
+      g_atb_trace[it][ev] = t_;                                        \
+    }                                                                  \
+  } while (0)
+#else
+#define ATB_STAMP(it, ev) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const __grid_constant__ CUtensorMap tmap_dqkv, const AttnBwdParams p) {
@@ -700,8 +717,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         for (int qt = 0; qt < nt; ++qt, ++it) {
           const float l2 = aux[qt * 128 + r];
           const float dl = aux[256 + qt * 128 + r];
+          ATB_STAMP(it, 0);
           mbar_wait(bar_s, it & 1);
           tc_fence_after();
+          ATB_STAMP(it, 1);
           uint32_t pk[2][16], dk[2][16];
           const bool rows_live = qt * 128 + quarter * 32 < p.N;  // warp-uniform
           bool consumed = false;
@@ -724,6 +743,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
               tc_fence_before();
               mbar_arrive(bar_c);
               consumed = true;
+              ATB_STAMP(it, 2);
             }
             if (key0 + 32 <= p.N) {  // whole chunk inside the sequence: no per-element masking
               const float dls = dl * p.scale;
@@ -757,10 +777,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
             tc_fence_before();
             mbar_arrive(bar_c);
           }
+          ATB_STAMP(it, 3);
           if (it > 0) {
             mbar_wait(bar_m2, (it - 1) & 1);  // previous MMA 2 retired: sP / sdS free, its dK / dV / dQ final
             tc_fence_after();
           }
+          ATB_STAMP(it, 4);
           // chunk ch = 2c + hf: column block ch >> 1 == c (64 keys each), 64-byte half ch & 1 == hf
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -778,7 +800,19 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
           tc_fence_before();
           mbar_arrive(bar_p);
+          ATB_STAMP(it, 5);
+          // What bounds this kernel (profiles/r2_attn_trace_bwd.txt): shared-memory bandwidth. Per cell the five
+          // products read 208 KB of operands and the math warps store 64 KB of P / dS — 2 100 cycles at 128 B per
+          // cycle; a full cell takes 2 200 - 2 800, and with the tile loads and the drains' staging an item moves
+          // ~1.4 MB = 11 000 of its 17 400 cycles. Tried against it in round 2, all measured, none kept: the next
+          // item's first scores issued behind this item's last bar_c (the 1 600 - 3 400 cycle wait at every item
+          // start shrinks to 1 000, the item takes as long); drains in 8-row steps through two staging halves
+          // (242 us), a coalesced LDS + STG flush instead of the tensor store (221 us); dedicated drain warps
+          // (16 warps at 128 registers, math warps storing P / dS per chunk: 226 us — the time moves from the
+          // drains to the wait for the previous cell's second MMA group, sP / sdS and the accumulators being
+          // single-buffered: shared and tensor memory are both full).
           drain();  // whatever finished with the previous iteration's MMA 2
+          ATB_STAMP(it, 6);
           if (qt == nt - 1) {
             pend_kv = true;
             kv_b = b; kv_h = h; kv_kb = kb;
@@ -1601,6 +1635,10 @@ int attention_tc_bwd_long(const void* qkv, const void* dout, const float* lse, c
 }  // namespace fv
 
 #ifdef ATC_TRACE
+extern "C" int fv_debug_read_trace_bwd(long long* dst) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(dst, fv::g_atb_trace, sizeof(fv::g_atb_trace)) == cudaSuccess ? 0 : -2;
+}
 extern "C" int fv_debug_read_trace(long long* dst, int64_t n) {
   cudaDeviceSynchronize();
   const size_t bytes = static_cast<size_t>(n) * sizeof(long long);
