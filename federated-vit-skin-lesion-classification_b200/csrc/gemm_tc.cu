@@ -313,6 +313,21 @@ __device__ __forceinline__ void chunk_to_stage(const f32x2 (&v)[16], uint8_t* st
   }
 }
 
+#ifdef GEMM_TRACE
+// measurement build (tools/build_variants.py gemm_tc.cu gtrace:-DGEMM_TRACE, tools/gemm_trace.py): SM-clock
+// timestamps of epilogue warp 4 of CTA 0 over its first 24 tiles — 0 arrives at the accumulator wait, 1 accumulator
+// there, 2 tile drained; 3 = cycles of that tile spent waiting for a tensor store to release the staging tile,
+// 4 = cycles between a tcgen05.ld and its data, 5 = cycles in the chunks' arithmetic (bias, activation), 6 = cycles in
+// stage_store (proxy fence, warp sync, tensor-store issue)
+__device__ long long g_gemm_trace[24][8];
+__device__ long long g_gemm_acq, g_gemm_ldw, g_gemm_math, g_gemm_store;
+#define GT_ON (blockIdx.x == 0 && threadIdx.x == 128)
+__device__ __forceinline__ long long gt_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+#endif
 // Epilogue of one 128 x 256 accumulator tile for one warp (its 32 TMEM lanes / rows).
 // Output path: each warp's staged 32-row x 128-byte segment (already in the TMA 128B-swizzle
 // layout) leaves through ONE tensor store issued by lane 0 — cp.async.bulk.tensor (plain outputs)
@@ -328,6 +343,9 @@ __device__ __forceinline__ void stage_store(const GemmTcParams& p, const CUtenso
     stage_flush<EPI>(stg, base, ld, p, g, lane);
     return;
   }
+#ifdef GEMM_TRACE
+  const long long ts0 = gt_clock();
+#endif
   fence_proxy_async_smem();  // generic-proxy writes of the tile -> visible to the TMA engine
   __syncwarp();
   if (lane == 0) {
@@ -339,12 +357,21 @@ __device__ __forceinline__ void stage_store(const GemmTcParams& p, const CUtenso
     tma_store_commit();
   }
   pending = true;
+#ifdef GEMM_TRACE
+  if (GT_ON) g_gemm_store += gt_clock() - ts0;
+#endif
 }
 __device__ __forceinline__ void stage_acquire(int lane, bool& pending) {
   if (pending) {
+#ifdef GEMM_TRACE
+    const long long t0 = gt_clock();
+#endif
     if (lane == 0) tma_store_wait_read();
     __syncwarp();
     pending = false;
+#ifdef GEMM_TRACE
+    if (GT_ON) g_gemm_acq += gt_clock() - t0;
+#endif
   }
 }
 
@@ -403,7 +430,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
                         ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q)
                         : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#ifdef GEMM_TRACE
+        const long long tl0 = gt_clock();
+#endif
         tmem_ld_wait();
+#ifdef GEMM_TRACE
+        if (GT_ON) g_gemm_ldw += gt_clock() - tl0;
+#endif
         f32x2 v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = f2_pack_u(r[2 * i], r[2 * i + 1]);
@@ -441,6 +474,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmTcParams& p, const CUten
             }
           }
         }
+#ifdef GEMM_TRACE
+        if (GT_ON) g_gemm_math += gt_clock() - tl0;
+#endif
         if (c == 0) stage_acquire(lane, pending);
         chunk_to_stage(v, stg, lane, c * (bf16 ? 4 : 8), bf16);
       }
@@ -1103,8 +1139,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int mn = tile % tiles_mn;
       const int m2 = mn / p.num_n_blocks;
       const int n_blk = mn - m2 * p.num_n_blocks;
+#ifdef GEMM_TRACE
+      const int gti = (tile - cluster_id) / num_clusters;
+      if (GT_ON && gti < 24) {
+        g_gemm_trace[gti][0] = gt_clock();
+        g_gemm_acq = 0;
+        g_gemm_ldw = 0;
+        g_gemm_math = 0;
+        g_gemm_store = 0;
+      }
+#endif
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+#ifdef GEMM_TRACE
+      if (GT_ON && gti < 24) g_gemm_trace[gti][1] = gt_clock();
+#endif
       const long long row0 = static_cast<long long>(m2) * 2 * BM + rank * BM + wq * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + half * (BN / 2);
       epilogue_tile<EPI, BF16>(p, &tmap_c, &tmap_aux, epi_stage + (warp - 4) * EPI_STAGE_BYTES, taddr, row0,
@@ -1112,6 +1161,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+#ifdef GEMM_TRACE
+      if (GT_ON && gti < 24) {
+        g_gemm_trace[gti][2] = gt_clock();
+        g_gemm_trace[gti][3] = g_gemm_acq;
+        g_gemm_trace[gti][4] = g_gemm_ldw;
+        g_gemm_trace[gti][5] = g_gemm_math;
+        g_gemm_trace[gti][6] = g_gemm_store;
+      }
+#endif
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (pending && lane == 0) tma_store_wait_all();
@@ -1480,3 +1538,10 @@ extern "C" int fv_linear_residual_bf16(const void* a, int64_t lda, const void* w
   fv::g_rows_per_scale = 0;
   return rc;
 }
+
+#ifdef GEMM_TRACE
+extern "C" int fv_debug_read_gemm_trace(long long* dst) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(dst, fv::g_gemm_trace, sizeof(fv::g_gemm_trace)) == cudaSuccess ? 0 : -2;
+}
+#endif

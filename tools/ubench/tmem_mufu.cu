@@ -149,6 +149,27 @@ __global__ void __launch_bounds__(512, 1) bench(int iters, long long* cycles, fl
     acc += __uint_as_float(x & 0xff);
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc += v[k];
+  } else if (mode == 8 || mode == 9) {
+    // 8: rcp.approx.ftz.f32 alone; 9: FFMA2-only Horner chains (packed fp32 pairs), 32 ops = 16 instructions
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 1.0f + 0.01f * (k + threadIdx.x);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        if (mode == 8) {
+          asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(v[k]) : "f"(v[k] + 1.f));
+          asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(v[k + 1]) : "f"(v[k + 1] + 1.f));
+        } else {
+          unsigned long long a, b = 0x3f8000003f800000ull, c = 0x3a83126f3a83126full;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(v[k]), "f"(v[k + 1]));
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a) : "l"(a), "l"(b), "l"(c));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(v[k]), "=f"(v[k + 1]) : "l"(a));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc += v[k];
   } else if (mode == 4) {
     uint32_t pk[16];
 #pragma unroll
@@ -168,7 +189,7 @@ template <int mode, int mix>
 void go(int g, int b, int iters, long long* cyc, float* sink) { bench<mode, mix><<<g, b>>>(iters, cyc, sink); }
 void launch(int mode, int mix, int g, int b, int iters, long long* cyc, float* sink) {
 #define CASE(m, x) if (mode == m && mix == x) return go<m, x>(g, b, iters, cyc, sink);
-  CASE(0, 0) CASE(1, 0) CASE(1, 4) CASE(1, 2) CASE(2, 0) CASE(3, 0) CASE(3, 4) CASE(3, 2) CASE(4, 0) CASE(5, 0) CASE(6, 0) CASE(7, 0)
+  CASE(0, 0) CASE(1, 0) CASE(1, 4) CASE(1, 2) CASE(2, 0) CASE(3, 0) CASE(3, 4) CASE(3, 2) CASE(4, 0) CASE(5, 0) CASE(6, 0) CASE(7, 0) CASE(8, 0) CASE(9, 0)
 }
 int main() {
   long long* cyc;
@@ -177,11 +198,11 @@ int main() {
   cudaMalloc(&sink, 148 * 2 * 512 * 4);
   long long h[148 * 2 * 16];
   const int iters = 256;
-  const char* names[] = {"tmem ld x32 (4 KB per warp-load)", "mufu ex2", "fma exp2", "softmax pass: ld + ex2 + cvt + st", "tmem st x16", "cvt.rn.bf16x2 (16 per 32 ops)", "ex2 + cvt.rn.bf16x2", "ex2 + iadd/prmt pack"};
+  const char* names[] = {"tmem ld x32 (4 KB per warp-load)", "mufu ex2", "fma exp2", "softmax pass: ld + ex2 + cvt + st", "tmem st x16", "cvt.rn.bf16x2 (16 per 32 ops)", "ex2 + cvt.rn.bf16x2", "ex2 + iadd/prmt pack", "mufu rcp", "fma.rn.f32x2 (two elements per op)"};
   for (int ctas = 1; ctas <= 2; ++ctas)
     for (int warps : {4, 8, 16}) {
       if (ctas == 2 && warps == 16) continue;
-      for (int mode = 0; mode < 8; ++mode)
+      for (int mode = 0; mode < 10; ++mode)
         for (int mix : {0, 4, 2}) {
           if (mix && mode != 1 && mode != 3) continue;
           for (int rep = 0; rep < 2; ++rep) {
