@@ -12,23 +12,28 @@ namespace fv {
 template <bool OUT_BF16>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, void* __restrict__ out, int batch, int chans,
-                int height, int width) {
+                int height, int width, int lead) {
   pdl_wait();
   const int gw = width >> 4, gh = height >> 4;
   const int kdim = chans * 256;
-  const long long total = static_cast<long long>(batch) * gh * gw * (kdim >> 2);
+  const int rows_per_img = gh * gw + lead;  // `lead` zero rows in front of every image's patches (the cls slot)
+  const long long total = static_cast<long long>(batch) * rows_per_img * (kdim >> 2);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int kq = static_cast<int>(i % (kdim >> 2));
     const long long row = i / (kdim >> 2);
-    const int pw = static_cast<int>(row % gw);
-    const int ph = static_cast<int>((row / gw) % gh);
-    const int b = static_cast<int>(row / (static_cast<long long>(gw) * gh));
-    const int px = (kq & 3) << 2;
-    const int py = (kq >> 2) & 15;
-    const int c = kq >> 6;
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(
-        img + ((static_cast<long long>(b) * chans + c) * height + (ph * 16 + py)) * width + pw * 16 + px));
+    const int tok = static_cast<int>(row % rows_per_img) - lead;
+    const int b = static_cast<int>(row / rows_per_img);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tok >= 0) {
+      const int pw = tok % gw;
+      const int ph = tok / gw;
+      const int px = (kq & 3) << 2;
+      const int py = (kq >> 2) & 15;
+      const int c = kq >> 6;
+      v = __ldcs(reinterpret_cast<const float4*>(
+          img + ((static_cast<long long>(b) * chans + c) * height + (ph * 16 + py)) * width + pw * 16 + px));
+    }
     if (OUT_BF16) {
       uint2 pk;
       pk.x = pack_bf16(v.x, v.y);
@@ -181,7 +186,13 @@ softmax_rows_bwd_kernel(const float* __restrict__ p, const float* __restrict__ d
 
 extern "C" int fv_patchify(const float* img, void* out, int out_dtype, int64_t batch, int64_t chans,
                            int64_t height, int64_t width, void* stream) {
+  return fv_patchify_rows(img, out, out_dtype, batch, chans, height, width, 0, stream);
+}
+
+extern "C" int fv_patchify_rows(const float* img, void* out, int out_dtype, int64_t batch, int64_t chans,
+                                int64_t height, int64_t width, int64_t lead_rows, void* stream) {
   using namespace fv;
+  FV_CHECK_ARG(lead_rows >= 0 && lead_rows <= 16, "fv_patchify_rows: lead_rows out of range");
   FV_CHECK_ARG(img && out, "fv_patchify: null pointer");
   FV_CHECK_ARG(batch > 0 && chans > 0 && height > 0 && width > 0 && height % 16 == 0 && width % 16 == 0,
                "fv_patchify: image %lldx%lldx%lldx%lld must have H, W multiples of 16",
@@ -189,15 +200,15 @@ extern "C" int fv_patchify(const float* img, void* out, int out_dtype, int64_t b
   FV_CHECK_ARG(out_dtype == FV_F32 || out_dtype == FV_BF16, "fv_patchify: bad out_dtype");
   FV_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "fv_patchify: pointers must be 16-byte aligned");
-  const long long total = batch * (height / 16) * (width / 16) * chans * 64;
+  const long long total = batch * ((height / 16) * (width / 16) + lead_rows) * chans * 64;
   long long want = ceil_div(total, 256 * 4);
   const long long cap = static_cast<long long>(num_sms()) * 16;
   const unsigned grid = static_cast<unsigned>(want < cap ? (want < 1 ? 1 : want) : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_dtype == FV_BF16)
-    FV_CHECK_CUDA(fv::launch_pdl(patchify_kernel<true>, dim3(grid), dim3(256), 0, st, img, out, (int)batch, (int)chans, (int)height, (int)width));
+    FV_CHECK_CUDA(fv::launch_pdl(patchify_kernel<true>, dim3(grid), dim3(256), 0, st, img, out, (int)batch, (int)chans, (int)height, (int)width, (int)lead_rows));
   else
-    FV_CHECK_CUDA(fv::launch_pdl(patchify_kernel<false>, dim3(grid), dim3(256), 0, st, img, out, (int)batch, (int)chans, (int)height, (int)width));
+    FV_CHECK_CUDA(fv::launch_pdl(patchify_kernel<false>, dim3(grid), dim3(256), 0, st, img, out, (int)batch, (int)chans, (int)height, (int)width, (int)lead_rows));
   FV_LAUNCH_CHECK();
   return FV_OK;
 }

@@ -366,23 +366,25 @@ def _(p, dp, scale):
 # patch embedding helpers, column sums
 # ------------------------------------------------------------------------------------------------
 @_op("fedvit::patchify", mutates_args=())
-def patchify(img: Tensor, out_bf16: bool) -> Tensor:
-    """NCHW fp32 image -> [B*(H/16)*(W/16), C*256] patch rows, (c, py, px) column order."""
+def patchify(img: Tensor, out_bf16: bool, lead_rows: int = 0) -> Tensor:
+    """NCHW fp32 image -> [B*(lead_rows + (H/16)*(W/16)), C*256] patch rows, (c, py, px) column order, with
+    ``lead_rows`` zero rows in front of every image's patches (1 = a cls slot: the rows line up with the
+    token rows of the residual stream)."""
     _need_cuda(img)
     if img.dtype != torch.float32 or img.dim() != 4:
         raise FedVitError("patchify: image must be fp32 NCHW")
     img = img.contiguous()
     b, c, h, w = img.shape
-    out = torch.empty((b * (h // 16) * (w // 16), c * 256), device=img.device,
+    out = torch.empty((b * (lead_rows + (h // 16) * (w // 16)), c * 256), device=img.device,
                       dtype=torch.bfloat16 if out_bf16 else torch.float32)
-    LIB.call("fv_patchify", img.data_ptr(), out.data_ptr(), _dt(out), b, c, h, w, _stream(img))
+    LIB.call("fv_patchify_rows", img.data_ptr(), out.data_ptr(), _dt(out), b, c, h, w, lead_rows, _stream(img))
     return out
 
 
 @patchify.register_fake
-def _(img, out_bf16):
+def _(img, out_bf16, lead_rows=0):
     b, c, h, w = img.shape
-    return img.new_empty((b * (h // 16) * (w // 16), c * 256),
+    return img.new_empty((b * (lead_rows + (h // 16) * (w // 16)), c * 256),
                          dtype=torch.bfloat16 if out_bf16 else torch.float32)
 
 

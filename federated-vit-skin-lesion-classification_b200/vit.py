@@ -467,11 +467,30 @@ class VisionTransformer(nn.Module):
             dx, dy = self._ln_bwd(dh, x, blk.norm1, mean1, rstd1, dx1, lp, branch_scale=prev_s2)
 
         # embedding: x0[b] = cat(cls, patches[b] W^T + b) + pos
+        proj = self.patch_embed.proj
+        if lp and st.patches is None and N == self.patch_embed.num_patches + 1:
+            # bf16 path after the im2col-free forward. The stream's gradient is contracted as it lies in memory:
+            # the patch rows are rebuilt with a zero row in every image's cls slot (fv_patchify_rows), so the
+            # weight gradient needs no copy of dy's patch rows (a strided 77 MB bf16 copy, 85 us per step), and
+            # ONE column sum over the batch, [N, D], carries the three small gradients: pos_embed (all of it),
+            # cls_token (row 0), the conv bias (rows 1 .. N - 1 summed) — from the fp32 gradient.
+            if self.pos_embed.requires_grad or self.cls_token.requires_grad or proj.bias.requires_grad:
+                tok = torch.empty(N * D, device=dev, dtype=torch.float32)
+                ops.colsum(dx.view(B, N * D), tok, False)
+                if self.pos_embed.requires_grad:
+                    _grad_buffer(self.pos_embed).view(N * D).add_(tok)
+                if self.cls_token.requires_grad:
+                    _grad_buffer(self.cls_token).view(D).add_(tok[:D])
+                if proj.bias.requires_grad:
+                    _grad_buffer(proj.bias).add_(tok.view(N, D)[1:].sum(0))
+            if proj.weight.requires_grad:
+                gw = _grad_buffer(proj.weight)
+                ops.wgrad(dy, ops.patchify(st.img, True, 1), gw.view(D, -1), None, _split_k_for(D, gw.numel() // D, M))
+            return
         if self.pos_embed.requires_grad:
             ops.colsum(dx.view(B, N * D), _grad_buffer(self.pos_embed).view(N * D), True)
         if self.cls_token.requires_grad:
             ops.colsum(dx.view(B, N * D)[:, :D], _grad_buffer(self.cls_token).view(D), True)
-        proj = self.patch_embed.proj
         if proj.weight.requires_grad or proj.bias.requires_grad:
             dpatch = dy.view(B, N, D)[:, 1:].reshape(B * (N - 1), D)
             if st.patches is None:  # the forward was im2col-free; the weight gradient wants patch rows

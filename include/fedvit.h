@@ -177,6 +177,12 @@ int fv_patch_embed_tf32(const float* img, const float* weight, const float* bias
                         int64_t dim, void* stream);
 int fv_patchify(const float* img, void* out, int out_dtype,
                 int64_t batch, int64_t chans, int64_t height, int64_t width, void* stream);
+/* the same with `lead_rows` zero rows in front of every image's patches: [B*(lead_rows + (H/16)*(W/16)), C*256].
+ * With lead_rows = 1 the rows line up with the token rows [B*N, D] of the residual stream (row 0 = the cls slot),
+ * so the patch-embedding weight gradient contracts the stream's gradient as it lies in memory — the cls rows meet
+ * zeros — instead of a copy of its patch rows (the backward of timm PatchEmbed.proj, model.py:193). */
+int fv_patchify_rows(const float* img, void* out, int out_dtype,
+                     int64_t batch, int64_t chans, int64_t height, int64_t width, int64_t lead_rows, void* stream);
 int fv_cls_pos_rows(const float* cls, const float* pos, float* x,
                     int64_t batch, int64_t tokens, int64_t dim, void* stream);
 
