@@ -606,3 +606,19 @@ def test_single_pass_attention_forward_vs_fp64(B, N, H, spread, late, monkeypatc
     d4 = ops.attention_bwd(qkv, out4, dout, lse4, B, N, H, scale).float()
     d1 = ops.attention_bwd(qkv, out1, dout, lse1, B, N, H, scale).float()
     assert float((d4 - d1).norm()) <= 1e-2 * float(d1.norm()) + 1e-6
+
+
+def test_patchify_rows_leaves_a_zero_cls_slot():
+    """fv_patchify_rows: the patch rows of fv_patchify with ``lead_rows`` zero rows in front of every image's
+    patches (the layout the patch-embedding weight gradient contracts against the token-major stream gradient)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.randn(3, 4, 32, 48, device=DEV, generator=g)
+    for bf in (False, True):
+        plain = ops.patchify(img, bf)
+        for lead in (1, 2):
+            full = ops.patchify(img, bf, lead).view(3, lead + 6, -1)
+            assert torch.equal(full[:, lead:].reshape(18, -1), plain)
+            assert not full[:, :lead].any()
+    # the reference unfold: rows in (c, py, px) order
+    ref = torch.nn.functional.unfold(img, 16, stride=16).transpose(1, 2).reshape(18, -1)
+    assert torch.equal(ops.patchify(img, False), ref)
