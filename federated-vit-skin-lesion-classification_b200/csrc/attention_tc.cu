@@ -542,13 +542,19 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           const uint64_t dS_mn = make_smem_desc_sw128(smem_u32(sdS), ATB_TILE, 1024);
           const uint64_t dS_k0 = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
           const int ks = kwb >> 4;
+          // dV / dK contract over the tile's queries: the ragged last tile (69 of 128 at N = 197) has P = dS = 0
+          // beyond the sequence, so only its first ceil(rows / 16) k-steps are issued (5 of 8: 36 KB less
+          // shared-memory operand traffic per such cell, and this kernel is bound by that traffic)
+          int qrows = p.N - qt * 128;
+          if (qrows > 128) qrows = 128;
+          const int qs = (qrows + 15) >> 4;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem + T_DV, dP_mn + k * 128, dO_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+              if (k < qs) umma_bf16(tmem + T_DV, dP_mn + k * 128, dO_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem + T_DK, dS_mn + k * 128, dQ_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
+              if (k < qs) umma_bf16(tmem + T_DK, dS_mn + k * 128, dQ_mn + k * 128, id_dvk, (qt > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               if (k < ks) {
